@@ -1,0 +1,170 @@
+"""Pins oracle/hdmoe_oracle.py against fixtures generated from the unmodified reference
+(tools/make_golden.py) and against the analytic invariants the reference's own tests state."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TINY, golden_weights, load_golden, rel_l2
+from oracle import hdmoe_oracle as O
+
+TOL = 2e-6   # fp32 CPU vs fp32 CPU, same library: differences are re-association only
+
+
+def _run_model(g, sd):
+    variant, k, train = g["meta.variant"], g["meta.top_k"], g["meta.train"]
+    cfg = dict(TINY, top_k=k)
+    sd = {k_: v.clone().requires_grad_(v.dtype.is_floating_point) for k_, v in sd.items()}
+    noise = None
+    if train:
+        draws = [g[f"noise.{i}"] for i in range(g["meta.n_noise"])]
+        # draw order: cfg1 prepends the scaling_net draw; then vit router, then U-Net router
+        noise = ({"scaling": draws[0], "vit": draws[1], "unet": draws[2]} if variant == 1
+                 else {"vit": draws[0], "unet": draws[1]})
+    x = g["in.x"].clone().requires_grad_(True)
+    cap = {}
+    import contextlib
+    with (O.training_mode() if train else contextlib.nullcontext()):
+        out = O.preconditioned(sd, cfg, x, g["in.sigma"], g["in.text"], g["in.unet_mask"], g["in.vit_mask"],
+                               zeta=g["in.zeta"], transition_point=-1.2, softness=1.6, return_log_var=True,
+                               noise=noise, variant=variant, capture=cap)
+    return sd, x, out, cap
+
+
+@pytest.mark.parametrize("case", ["cfg2_train_k2", "cfg2_eval_k1", "cfg1_train_k1", "cfg1_eval_k2"])
+def test_model_forward_backward_matches_reference(case):
+    g = load_golden(case)
+    sd, x, out, cap = _run_model(g, golden_weights(g))
+    for key in ("denoised", "Unet_router_loss", "vit_router_loss", "scaling_net_out", "out_gate", "log_var"):
+        assert rel_l2(out[key], g["out." + key]) < TOL, key
+    for key in ("Unet_raw", "vit_raw"):
+        ref = g["out." + key]
+        assert torch.equal(torch.isinf(out[key]), torch.isinf(ref))
+        fin = torch.isfinite(ref)
+        assert rel_l2(out[key][fin], ref[fin]) < TOL, key
+    # bit-exact integer contract: routing assignment and dispatch order
+    for rn, w in (("Unet_router", cap["w_unet"]), ("vit_router", cap["w_vit"])):
+        _, _, src, exp = O.dispatch_plan(w)
+        assert np.array_equal(src, g[f"router.{rn}.src_row"].numpy())
+        assert np.array_equal(exp, g[f"router.{rn}.expert_of_row"].numpy())
+        assert torch.equal(w > 0, g[f"router.{rn}.sparse"] > 0)
+        assert rel_l2(w, g[f"router.{rn}.sparse"]) < TOL
+    loss = O.edm_loss(g["in.x0"], out, 4, 0.05, 0.1, 0.005)
+    for key in ("loss", "denoising", "balance", "z_loss", "pure_loss"):
+        assert abs(float(loss[key]) - float(g["loss." + key])) < 1e-5 * max(1.0, abs(float(g["loss." + key]))), key
+    loss["loss"].backward()
+    assert rel_l2(x.grad, g["grad.x"]) < 2e-5
+    for k_, v in g.items():
+        if k_.startswith("grad.") and k_ != "grad.x":
+            got = sd[k_[5:]].grad
+            got = torch.zeros_like(v) if got is None else got
+            if float(v.abs().max()) == 0:
+                assert float(got.abs().max()) < 1e-9, k_
+            else:
+                assert rel_l2(got, v) < 5e-5, k_
+    for k_, v in g.items():
+        if k_.startswith("sd_after."):
+            assert rel_l2(sd[k_[9:]].detach(), v) < 1e-6, k_
+
+
+@pytest.mark.parametrize("case", ["sampler_cfg2_g1", "sampler_cfg2_g2_churn"])
+def test_sampler_matches_reference(case):
+    g = load_golden(case)
+    sd = golden_weights(g)
+    cfg = dict(TINY, top_k=1)
+    fn = O.make_denoiser(sd, cfg, g["in.text"], -1.2, 1.6, guidance=g["meta.guidance"],
+                         uncond_text_emb=g["in.uncond"])
+    draws = [g[f"noise.{i}"] for i in range(g["meta.n_noise"])]
+    assert len(draws) == g["meta.num_steps"]          # randn_like is drawn every step (quirk Q14)
+    with torch.no_grad():
+        x = O.edm_sample(fn, g["in.noise"], num_steps=g["meta.num_steps"], S_churn=g["meta.S_churn"],
+                         S_noise=g["meta.S_noise"], step_noise=draws)
+    assert rel_l2(x, g["out.x"]) < 5e-5
+
+
+def test_router_tail_matches_reference():
+    g = load_golden("router_tail")
+    for tag in "abcd":
+        k = g[f"{tag}.k"]
+        sp, gp, lg, idx = O.router_tail(g[f"{tag}.pooled"], g[f"{tag}.time_emb"], g[f"{tag}.w_time"],
+                                        g[f"{tag}.w_lin"], k, noise=g[f"{tag}.noise"], zeta=g[f"{tag}.zeta"],
+                                        mask=g[f"{tag}.mask"])
+        ref_lg = g[f"{tag}.logits"]
+        assert torch.equal(torch.isinf(lg), torch.isinf(ref_lg))
+        fin = torch.isfinite(ref_lg)
+        assert rel_l2(lg[fin], ref_lg[fin]) < TOL
+        live = g[f"{tag}.mask"].sum(1) > 0
+        assert torch.isnan(gp[~live]).all() and torch.isnan(g[f"{tag}.probs"][~live]).all()
+        assert rel_l2(gp[live], g[f"{tag}.probs"][live]) < TOL
+        assert rel_l2(sp[live], g[f"{tag}.sparse"][live]) < TOL
+        # indices bit-exact wherever the reference's choice is determined (live rows, finite picks)
+        ref_idx = g[f"{tag}.topk_idx"].long()
+        picked_fin = torch.gather(ref_lg, 1, ref_idx).isfinite()
+        assert torch.equal(idx[picked_fin], ref_idx[picked_fin])
+        assert abs(float(O.load_balance(torch.nan_to_num(gp), gp.shape[1])) - float(g[f"{tag}.load_balance"])) < 1e-5
+        assert abs(float(O.z_loss(lg)) - float(g[f"{tag}.z_loss"])) < 1e-4
+
+
+def test_moe_layer_matches_reference():
+    g = load_golden("moe_identity")
+    for tag in "abc":
+        x, te, txt, w = g[f"{tag}.x"], g[f"{tag}.time"], g[f"{tag}.text"], g[f"{tag}.w"]
+        out = O.moe_layer(x, w, te, txt, lambda e, xe, t, tx: xe * float(e + 1) + t.mean(1).view(-1, 1, 1, 1)
+                          + tx.mean(1).view(-1, 1, 1, 1))
+        assert torch.equal(out, g[f"{tag}.out"])          # fp32 mul-then-add in expert order: bit-exact
+        _, _, src, exp = O.dispatch_plan(w)
+        assert np.array_equal(src, g[f"{tag}.src_row"].numpy())
+        assert np.array_equal(exp, g[f"{tag}.expert_of_row"].numpy())
+
+
+def test_producers_match_reference():
+    g = load_golden("producers")
+    sigma = g["mask.sigma"]
+    for tag, attrs, rng in (("unet", [3, 3, 5, 5], (0.0, 0.6)), ("vit", [4, 8, 8, 16], (0.4, 1.0))):
+        c = O.expert_centers(attrs, rng)
+        assert torch.equal(c, g[f"mask.{tag}.centers"])
+        for step in (0, 700, 2600, 6000):
+            bw = O.mask_bandwidth(step, 0.3, 0.8, 5000, 0.1, "step")
+            assert torch.equal(O.band_mask(sigma, c, bw, -1.2, 1.6, 1), g[f"mask.{tag}.{step}"])
+    for i, s in enumerate(g["zeta.steps"].tolist()):
+        assert abs(O.zeta_schedule(s, 900, 2, 0.01, "cos", 4.0, 0.05) - float(g["zeta.cos"][i])) < 1e-12
+        assert abs(O.zeta_schedule(s, 900, 2, 0.01, "exp", 4.0, 0.05) - float(g["zeta.exp"][i])) < 1e-12
+    assert torch.equal(O.edm_schedule(18, 0.002, 80, 7)[:-1], g["sampler.t_steps18"])
+    x = O.edm_sample(lambda x, s: x * 0.9, g["sampler.noise"], num_steps=18)
+    assert rel_l2(x, g["sampler.mock09"]) < 1e-6
+    one, zero = torch.ones_like(g["sampler.noise"]), torch.zeros_like(g["sampler.noise"])
+    assert torch.equal(O.cfg_denoise(one, zero, 3.0), g["sampler.cfg3_denoise"])      # 0 + 3*(1-0) = 3
+    x = O.edm_sample(lambda x, s: O.cfg_denoise(torch.ones_like(x), torch.zeros_like(x), 3.0),
+                     g["sampler.noise"], num_steps=6)
+    assert rel_l2(x, g["sampler.cfg3"]) < 1e-6
+
+
+def test_primitives_match_reference():
+    g = load_golden("primitives")
+    for tag in ("lin", "c1", "c3", "c5", "c2"):
+        w, x = g[f"mpconv.{tag}.w"], g[f"mpconv.{tag}.x"]
+        assert rel_l2(O.mp_conv(x, w, 0.7), g[f"mpconv.{tag}.y"]) < TOL
+        sd = {"m.weights": w.clone()}
+        O.forced_weight_norm_(sd)
+        assert rel_l2(sd["m.weights"], g[f"mpconv.{tag}.w_after"]) < 1e-7
+        assert rel_l2(O.mp_conv(x, sd["m.weights"], 0.7), g[f"mpconv.{tag}.y_train"]) < TOL
+    assert rel_l2(O.resample(g["resample.x"], "down"), g["resample.down"]) < 1e-7
+    assert torch.equal(O.resample(g["resample.x"], "up"), g["resample.up"])
+    a, b = g["mp.a"], g["mp.b"]
+    assert rel_l2(O.mp_cat(a, b, 1, 0.3), g["mp.cat"]) < 1e-7
+    assert rel_l2(O.mp_sum(a, a * 2 + 1, 0.3), g["mp.sum"]) < 1e-7
+    assert rel_l2(O.mp_silu(a), g["mp.silu"]) < 1e-7
+
+
+def test_reference_invariants():
+    """Analytic invariants from the reference's own tests."""
+    E = 4
+    assert abs(float(O.load_balance(torch.full((16, E), 1.0 / E), E)) - 1.0) < 1e-6   # test_loss_1.py:88-89
+    lg = torch.randn(32, 6)
+    sp, gp, _, idx = O.router_gate_from_logits(lg, 2)
+    assert torch.allclose(gp.sum(1), torch.ones(32), atol=1e-6)
+    assert ((sp > 0).sum(1) == 2).all() and torch.allclose(sp.sum(1), torch.ones(32), atol=1e-6)   # test_routers.py:83-107
+    m = torch.ones(8, 6)
+    m[:, 2] = 0
+    sp, _, _, _ = O.router_gate_from_logits(torch.randn(8, 6).masked_fill(m == 0, float("-inf")), 2)
+    assert (sp[:, 2] == 0).all()
+    assert float(O.z_loss(torch.full((4, 3), 5.0))) < float(O.z_loss(torch.full((4, 3), 8.0)))
