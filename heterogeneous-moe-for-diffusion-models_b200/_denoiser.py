@@ -1,0 +1,195 @@
+"""Denoiser assembly shared by model_config1 / model_config2 (ref models/model_config{1,2}.py):
+router_to_unet_experts (dispatch -> experts -> combine), HDMOEM and the EDM-preconditioned wrapper."""
+import math
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import model_components as mc
+from . import model_internals as util
+from . import ops
+
+# dtype of the expert path (dispatch payload, expert activations, combine input).  The reference only runs
+# fp32 (quirks Q16); bf16 here is the B200 training configuration of BASELINE.json.
+_EXPERT_DTYPE = [torch.float32]
+
+
+def set_expert_dtype(dtype: torch.dtype) -> None:
+    assert dtype in (torch.float32, torch.bfloat16)
+    _EXPERT_DTYPE[0] = dtype
+
+
+def get_expert_dtype() -> torch.dtype:
+    return _EXPERT_DTYPE[0]
+
+
+def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: torch.Tensor,
+                           time_emb: torch.Tensor, text_emb: Optional[torch.Tensor],
+                           top_k: Optional[int] = None) -> torch.Tensor:
+    """One MoE layer: same signature and result as the reference helper (models/model_config2.py:11-39).
+
+    dispatch plan (bit-exact, expert-major / token-ascending, criterion weight > 0) -> ONE fused gather of
+    the image rows, time rows and mean-pooled text rows -> experts on contiguous row ranges -> ONE
+    gate-weighted combine (ascending expert order, fp32 accumulate).  A single device->host copy of the
+    E+1 offsets replaces the reference's >= 2E syncs."""
+    if text_emb is not None and text_emb.ndim == 3:
+        text_emb = text_emb.mean(dim=1)
+    dt = get_expert_dtype()
+    plan = ops.dispatch_plan(out_router, top_k)
+    srcs = [x.to(dt), time_emb.to(dt)] + ([text_emb.to(dt)] if text_emb is not None else [])
+    rows = ops.permute(plan, *srcs)
+    xr, tr = rows[0], rows[1]
+    txr = rows[2] if text_emb is not None else None
+    off = plan.host_offsets()
+    outs = []
+    for e, expert in enumerate(experts):
+        lo, hi = off[e], off[e + 1]
+        if hi == lo:
+            continue
+        outs.append(expert(x=xr[lo:hi], time_emb=tr[lo:hi], text_emb=None if txr is None else txr[lo:hi]))
+    R = off[-1]
+    if R < plan.cap:   # unused tail rows (tokens dispatched to fewer than K experts)
+        outs.append(xr.new_zeros((plan.cap - R,) + tuple(xr.shape[1:])))
+    out_rows = torch.cat(outs, dim=0) if len(outs) != 1 else outs[0]
+    return ops.combine(out_rows, out_router, plan, base=None, out_dtype=x.dtype)
+
+
+class HDMOEM(nn.Module):
+    """Hybrid diffusion MoE denoiser.  variant 2 = models/model_config2.py:42-303 (analytic sigma-sigmoid
+    path scaling), variant 1 = models/model_config1.py:42-309 (learned Scaling_router + soft query/context
+    swap).  Attribute names and state_dict keys follow the reference."""
+
+    _variant = 2
+
+    def __init__(self, IN_in_channels: int, IN_img_resolution: int, internal_channels: int, time_emb_dim: int,
+                 text_emb_dim: int, num_experts: int, top_k: int, Fourier_bandwidth: float, VIT_num_blocks: int,
+                 VIT_patch_sizes: List[int], VIT_num_groups: int, VIT_num_heads: int, VIT_emb_size: int,
+                 Unet_num_blocks: int, Unet_channel_mult: List[int], Unet_kernel_sizes: List[Tuple[int, int]],
+                 Unet_model_channels: Optional[int] = 192, Unet_channel_mult_emb: Optional[int] = None,
+                 Unet_label_balance: Optional[float] = 0.5, Unet_concat_balance: Optional[float] = 0.5):
+        super().__init__()
+        C = self.internal_channels = internal_channels
+        self.top_k = top_k
+        self.input_proj = util.MP_Conv(IN_in_channels, C, kernel=(3, 3))
+        self.Fourier_emb = util.MP_Fourier(num_channels=time_emb_dim // 2, bandwidth=Fourier_bandwidth)
+        self.out_fourier1 = util.MP_Conv(time_emb_dim // 2, time_emb_dim * 2, kernel=())
+        self.out_fourier2 = util.MP_Conv(time_emb_dim * 2, time_emb_dim, kernel=())
+        if self._variant == 1:
+            self.scaling_net = mc.Scaling_router(emb_dim=time_emb_dim, num_experts=2)
+        self.Unet_router = mc.Router(in_channels=C, time_dim=time_emb_dim, top_k=top_k, num_experts=num_experts)
+        self.vit_router = mc.Router(in_channels=C, time_dim=time_emb_dim, top_k=top_k, num_experts=num_experts)
+        self.alpha_txt = nn.Parameter(torch.tensor(0.0))
+        self.Unet_experts = nn.ModuleList(
+            mc.Unet_expert(img_resolution=IN_img_resolution, img_channels=C, time_emb_dim=time_emb_dim,
+                           text_emb_dim=text_emb_dim, num_blocks=Unet_num_blocks, channel_mult=Unet_channel_mult,
+                           kernel_size=Unet_kernel_sizes[i], label_balance=Unet_label_balance,
+                           concat_balance=Unet_concat_balance, model_channels=Unet_model_channels,
+                           channel_mult_emb=Unet_channel_mult_emb) for i in range(num_experts))
+        self.VIT_experts = nn.ModuleList(
+            mc.Vit_expert(num_heads=VIT_num_heads, num_groups=VIT_num_groups, in_channels=C,
+                          seq_ln=math.ceil(IN_img_resolution / VIT_patch_sizes[i]) ** 2, emb_dim=VIT_emb_size,
+                          num_blocks=VIT_num_blocks, patch_size=VIT_patch_sizes[i], text_dim=text_emb_dim,
+                          time_dim=time_emb_dim) for i in range(num_experts))
+        self.cross_attn = util.MP_Attention(num_heads=VIT_num_heads, emb_dim=C, seq_ln=IN_img_resolution ** 2,
+                                            context_dim=C, attn_balance=0.5, is_cross_attn=True)
+        self.cross_attn_text = util.MP_Attention(num_heads=VIT_num_heads, emb_dim=C, seq_ln=IN_img_resolution ** 2,
+                                                 context_dim=text_emb_dim, attn_balance=0.5, is_cross_attn=True)
+        self.gate1 = util.MP_Conv(C * 2, C, kernel=(1, 1))
+        self.gate2 = util.MP_Conv(C, 2, kernel=(1, 1))
+        self.output_proj = util.MP_Conv(C, IN_in_channels, kernel=(3, 3))
+
+    def _forward(self, x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point=None,
+                 softness=None, alpha_routing: float = 10, noise: Optional[dict] = None):
+        noise = noise or {}
+        B, _, H, W = x.shape
+        te = self.out_fourier1(self.Fourier_emb(time_vec))
+        te = self.out_fourier2(util.mp_silu(te))
+        feats = self.input_proj(x)
+        if self._variant == 2:      # models/model_config2.py:244-249
+            vw = torch.sigmoid((time_vec * 4 - transition_point) / softness).view(-1, 1, 1, 1)
+            s_vit = (vw + 1e-2) * 2
+            s_unet = ((1.0 - vw) + 1e-2) * 2
+            scaling = torch.cat([s_vit, s_unet], dim=1).view(-1, 2)
+        else:                       # models/model_config1.py:246-249
+            scaling = self.scaling_net(x=te, zeta=zeta, noise=noise.get("scaling"))
+            s_vit = scaling[:, 0:1].view(-1, 1, 1, 1)
+            s_unet = scaling[:, 1:2].view(-1, 1, 1, 1)
+        in_unet = s_unet * feats
+        in_vit = s_vit * feats
+        # the ViT router is evaluated first (RNG order, quirk Q2)
+        w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
+                                                noise=noise.get("vit"))
+        w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
+                                              noise=noise.get("unet"))
+        out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k)
+        out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k)
+        uf = out_u.flatten(2).transpose(1, 2)
+        vf = out_v.flatten(2).transpose(1, 2)
+        if self._variant == 2:
+            q, ctx = uf, vf
+        else:                       # models/model_config1.py:277-283
+            stronger = torch.sigmoid(alpha_routing * (s_vit - s_unet)).view(-1, 1, 1)
+            q = stronger * vf + (1 - stronger) * uf
+            ctx = stronger * uf + (1 - stronger) * vf
+        a = self.cross_attn(query=q, context=ctx, gain_s=1.0, gain_t=1.0)
+        b = self.cross_attn_text(query=a, context=text_emb, gain_s=1.0, gain_t=1.0)
+        fin = a + self.alpha_txt * (b - a)
+        img = fin.transpose(1, 2).reshape(B, self.internal_channels, H, W)
+        g = self.gate2(util.mp_silu(self.gate1(util.mp_cat(out_u, img, dim=1))))
+        g = F.softmax(g, dim=1)
+        gated = g[:, 0:1] * out_u + g[:, 1:2] * img
+        out = self.output_proj(util.mp_sum(out_u, gated, t=0.5))
+        return out, p_un, raw_un, p_vit, raw_vit, scaling, g
+
+
+class preconditioned_HDMOEM(nn.Module):
+    """EDM preconditioning wrapper (ref models/model_config2.py:306-468).  c_in scaling and the
+    c_skip/c_out output mix are fused elementwise kernels (ops.edm_precond_in/out); quirk Q1 (the skip uses
+    the already scaled input) is preserved."""
+
+    _net_cls = HDMOEM
+
+    def __init__(self, IN_in_channels: int, IN_img_resolution: int, internal_channels: int, time_emb_dim: int,
+                 text_emb_dim: int, num_experts: int, top_k: int, Fourier_bandwidth: float, VIT_num_blocks: int,
+                 VIT_patch_sizes: List[int], VIT_num_groups: int, VIT_num_heads: int, VIT_emb_size: int,
+                 Unet_num_blocks: int, Unet_channel_mult: List[int], Unet_kernel_sizes: List[Tuple[int, int]],
+                 Unet_model_channels: Optional[int] = 192, Unet_channel_mult_emb: Optional[int] = None,
+                 Unet_label_balance: Optional[float] = 0.5, Unet_concat_balance: Optional[float] = 0.5,
+                 sigma_data: Optional[float] = 0.5, log_var_channels: Optional[int] = 128):
+        super().__init__()
+        self.sigma_data = sigma_data
+        self.log_var_channels = log_var_channels
+        self.num_experts = num_experts
+        self.log_var_fourier = util.MP_Fourier(num_channels=log_var_channels)
+        self.log_var_linear = util.MP_Conv(log_var_channels, 1, kernel=())
+        self.net = self._net_cls(IN_in_channels=IN_in_channels, IN_img_resolution=IN_img_resolution,
+                                 internal_channels=internal_channels, time_emb_dim=time_emb_dim,
+                                 text_emb_dim=text_emb_dim, num_experts=num_experts, top_k=top_k,
+                                 Fourier_bandwidth=Fourier_bandwidth, VIT_num_blocks=VIT_num_blocks,
+                                 VIT_patch_sizes=VIT_patch_sizes, VIT_num_groups=VIT_num_groups,
+                                 VIT_num_heads=VIT_num_heads, VIT_emb_size=VIT_emb_size,
+                                 Unet_num_blocks=Unet_num_blocks, Unet_channel_mult=Unet_channel_mult,
+                                 Unet_kernel_sizes=Unet_kernel_sizes, Unet_model_channels=Unet_model_channels,
+                                 Unet_channel_mult_emb=Unet_channel_mult_emb, Unet_label_balance=Unet_label_balance,
+                                 Unet_concat_balance=Unet_concat_balance)
+
+    def _forward(self, x, sigma, text_emb, Unet_router_mask, Vit_router_mask, zeta, return_log_var=False,
+                 precomputed_x_in: Optional[torch.Tensor] = None, raw_output: bool = False, **net_kw):
+        sigma = sigma.to(torch.float32)
+        c_noise = sigma.flatten().log() / 4
+        B = x.shape[0]
+        if c_noise.shape[0] == 1 and B > 1:
+            c_noise = c_noise.expand(B)
+        x_in = precomputed_x_in if precomputed_x_in is not None else ops.edm_precond_in(x, sigma, self.sigma_data)
+        out_net, p_un, raw_un, p_vit, raw_vit, scaling, gate = self.net(
+            x=x_in, text_emb=text_emb, time_vec=c_noise, Unet_router_mask=Unet_router_mask,
+            Vit_router_mask=Vit_router_mask, zeta=zeta, **net_kw)
+        # raw_output: the fused Heun kernels apply c_skip / c_out themselves (EDM_sampler.py fast path)
+        D_x = out_net if raw_output else ops.edm_precond_out(x_in, out_net, sigma, self.sigma_data)
+        log_var = None
+        if return_log_var:
+            log_var = self.log_var_linear(self.log_var_fourier(c_noise)).reshape(-1, 1, 1, 1)
+        return {"denoised": D_x, "Unet_router_loss": p_un, "Unet_raw": raw_un, "vit_router_loss": p_vit,
+                "vit_raw": raw_vit, "scaling_net_out": scaling, "out_gate": gate, "log_var": log_var}

@@ -1,0 +1,72 @@
+"""ctypes binding of libhdmoe_b200.so (the C ABI declared in include/hdmoe_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhdmoe_b200.so")
+
+F32, BF16 = 0, 1
+MAX_EXPERTS, MAX_TOPK = 64, 8
+WLAYOUT_SAME, WLAYOUT_TAPS = 0, 1
+
+_p, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+
+
+class WprepDesc(C.Structure):
+    _fields_ = [("w", _p), ("w_hat", _p), ("gain_ptr", _p), ("gain", _f), ("rows", C.c_int32), ("fan_in", C.c_int32),
+                ("cin", C.c_int32), ("taps", C.c_int32), ("cin_pad", C.c_int32), ("out_dtype", C.c_int32),
+                ("layout", C.c_int32), ("block_start", C.c_int32)]
+
+
+# name -> (restype, argtypes); mirrors include/hdmoe_b200.h one to one
+PROTOTYPES = {
+    "hdmoe_version": (_i, []),
+    "hdmoe_last_error": (C.c_char_p, []),
+    "hdmoe_launch_count": (_i64, []),
+    "hdmoe_router_gate_workspace_bytes": (_sz, [_i, _i]),
+    "hdmoe_router_gate_fwd": (_i, [_p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hdmoe_router_gate_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "hdmoe_dispatch_plan_workspace_bytes": (_sz, [_i, _i]),
+    "hdmoe_dispatch_plan": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hdmoe_permute_rows": (_i, [_p, _p, _p, _i, _p, _p, _i, _p]),
+    "hdmoe_combine_rows": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i64, _p]),
+    "hdmoe_combine_rows_bwd": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i64, _p, _p, _p]),
+    "hdmoe_edm_precond_in": (_i, [_p, _p, _i, _f, _p, _i, _i64, _i64, _p]),
+    "hdmoe_edm_precond_out": (_i, [_p, _i, _p, _i, _p, _i, _f, _p, _i64, _i64, _p]),
+    "hdmoe_edm_precond_out_bwd": (_i, [_p, _p, _i, _f, _p, _i, _p, _i, _i64, _i64, _p]),
+    "hdmoe_edm_precond_in_bwd": (_i, [_p, _i, _p, _i, _f, _p, _i64, _i64, _p]),
+    "hdmoe_edm_heun_pre": (_i, [_p, _p, _f, _f, _f, _p, _p, _i, _i64, _p]),
+    "hdmoe_edm_heun_euler": (_i, [_p, _p, _i, _p, _p, _i, _f, _f, _f, _f, _p, _p, _p, _i64, _p]),
+    "hdmoe_edm_heun_correct": (_i, [_p, _p, _p, _i, _p, _p, _i, _f, _f, _f, _f, _p, _p, _i64, _p]),
+    "hdmoe_wprep_fwd": (_i, [_p, _p, _i, _i, _p]),
+    "hdmoe_wprep_bwd": (_i, [_p, _p, _p, _f, _i, _i, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (loads on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+                               "hdmoe_b200 has no CPU or eager fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(_lib, name)      # AttributeError here == header/library mismatch
+            fn.restype, fn.argtypes = res, args
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().hdmoe_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count():
+    return int(lib().hdmoe_launch_count())

@@ -1,0 +1,524 @@
+// PERMUTE / COMBINE: bit-exact dispatch-plan build, HBM row gather, gate-weighted combine and their
+// backward.  Replaces the per-expert boolean-mask loop of router_to_unet_experts
+// (models/model_config2.py:23-37): nonzero()/index/index_put_ x E with >= 2E host syncs become a plan
+// (integer, bit-exact) plus one gather and one combine launch, no host sync.
+//
+// Roofline: HBM.  Algorithmic bytes: permute R*rowbytes read + written (+4 B index per
+// row); combine reads R*D*s + R*8 and writes T*D*s.
+#include "common.cuh"
+
+namespace hdmoe {
+
+// ---------------------------------------------------------------------------------------------------
+// Dispatch plan.  Stable counting sort of the (token, expert) pairs with sparse_w > 0 by expert.
+//   pass 1 (count)   : per 256-token tile, per-expert counts -> tilecnt[e][tile]
+//   pass 2 (scan)    : exclusive scan over the expert-major (e, tile) array -> tileoff, counts, offsets
+//   pass 3 (scatter) : ballot ranks inside the tile give each pair its row; writes row_src / row_expert /
+//                      row_w / tok_rows.
+// One thread owns one token and keeps its E selection flags in a 64-bit register mask.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPlanThreads = 256;
+
+__device__ __forceinline__ unsigned long long token_mask(const float* __restrict__ w, int t, int T, int E) {
+    unsigned long long m = 0ull;
+    if (t < T) {
+        const float* r = w + (size_t)t * E;
+        for (int e = 0; e < E; ++e)
+            if (__ldg(r + e) > 0.f) m |= 1ull << e;   // NaN > 0 is false (quirk Q3)
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(kPlanThreads)
+plan_count_kernel(const float* __restrict__ w, int T, int E, int ntiles, int32_t* __restrict__ tilecnt) {
+    __shared__ int cnt[HDMOE_MAX_EXPERTS];
+    if (threadIdx.x < E) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = blockIdx.x * kPlanThreads + threadIdx.x;
+    const unsigned long long m = token_mask(w, t, T, E);
+    const int lane = threadIdx.x & 31;
+    for (int e = 0; e < E; ++e) {
+        const unsigned b = __ballot_sync(0xffffffffu, (m >> e) & 1ull);
+        if (lane == 0 && b) atomicAdd(&cnt[e], __popc(b));
+    }
+    __syncthreads();
+    if (threadIdx.x < E) tilecnt[(size_t)threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// single block, 1024 threads: exclusive scan of n = E*ntiles ints (expert-major)
+__global__ void __launch_bounds__(1024)
+plan_scan_kernel(const int32_t* __restrict__ tilecnt, int E, int ntiles, int cap, int32_t* __restrict__ tileoff,
+                 int32_t* __restrict__ counts, int32_t* __restrict__ offsets, int32_t* __restrict__ status) {
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    const int n = E * ntiles;
+    const int per = (n + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, n);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += tilecnt[i];
+    // block exclusive scan of s
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = wsum[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += u;
+        }
+        wsum[lane] = iv - v;
+        if (lane == 31) carry_s = iv;
+    }
+    __syncthreads();
+    int run = wsum[warp] + incl - s;
+    for (int i = lo; i < hi; ++i) {
+        const int c = tilecnt[i];
+        tileoff[i] = run;
+        if (i % ntiles == 0) offsets[i / ntiles] = run;
+        run += c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        offsets[E] = carry_s;
+        status[0] = carry_s > cap ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x < E) counts[threadIdx.x] = offsets[threadIdx.x + 1] - offsets[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kPlanThreads)
+plan_scatter_kernel(const float* __restrict__ w, int T, int E, int ntiles, int cap, int K,
+                    const int32_t* __restrict__ tileoff, int32_t* __restrict__ row_src,
+                    int32_t* __restrict__ row_expert, float* __restrict__ row_w, int32_t* __restrict__ tok_rows,
+                    int32_t* __restrict__ status) {
+    __shared__ int warpoff[kPlanThreads / 32][HDMOE_MAX_EXPERTS];
+    const int t = blockIdx.x * kPlanThreads + threadIdx.x;
+    const unsigned long long m = token_mask(w, t, T, E);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = 0; e < E; ++e) {
+        const unsigned b = __ballot_sync(0xffffffffu, (m >> e) & 1ull);
+        if (lane == 0) warpoff[warp][e] = __popc(b);
+    }
+    __syncthreads();
+    if (threadIdx.x < E) {   // exclusive scan over warps, per expert, seeded with the tile's global offset
+        int run = tileoff[(size_t)threadIdx.x * ntiles + blockIdx.x];
+        for (int wv = 0; wv < kPlanThreads / 32; ++wv) {
+            const int c = warpoff[wv][threadIdx.x];
+            warpoff[wv][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    int slot = 0;
+    for (int e = 0; e < E; ++e) {
+        const bool sel = (m >> e) & 1ull;
+        const unsigned b = __ballot_sync(0xffffffffu, sel);
+        if (sel) {
+            const int pos = warpoff[warp][e] + __popc(b & ((1u << lane) - 1u));
+            if (pos < cap) {
+                row_src[pos] = t;
+                row_expert[pos] = e;
+                row_w[pos] = w[(size_t)t * E + e];
+            }
+            if (slot < K) tok_rows[(size_t)t * K + slot] = pos < cap ? pos : -1;
+            else status[0] = 2;
+            ++slot;
+        }
+    }
+    if (t < T)
+        for (; slot < K; ++slot) tok_rows[(size_t)t * K + slot] = -1;
+}
+
+// fills the unused tail [R, cap) so that fixed-size consumers see well-defined values
+__global__ void plan_tail_kernel(const int32_t* __restrict__ offsets, int E, int cap, int32_t* __restrict__ row_src,
+                                 int32_t* __restrict__ row_expert, float* __restrict__ row_w) {
+    const int R = offsets[E];
+    for (int i = R + blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        row_src[i] = -1;
+        row_expert[i] = -1;
+        row_w[i] = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Row gather.  Two paths:
+//  * bulk: rows >= 4 KiB move as cp.async.bulk global->shared->global (the TMA engine does the copy, one
+//    elected thread per CTA drives a 4-deep ring of 16 KiB buffers);
+//  * vector: a warp copies a row chunk with 128-bit streaming loads/stores, 4 in flight per lane.
+// ---------------------------------------------------------------------------------------------------
+struct PermuteArgs {
+    const char* src[4];
+    char* dst[4];
+    long long row_bytes[4];
+    long long chunks_per_row[4];   // chunk = kChunk bytes
+    long long chunk_base[4];       // first global chunk id of tensor i (for one row-set)
+    int n_tensors;
+};
+
+constexpr int kChunk = 16384;
+constexpr int kBulkStages = 6;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+// one work item = (row r, tensor i, chunk c); items are enumerated tensor-major per row so that the big
+// payload rows dominate and every CTA streams contiguous 16 KiB pieces.
+__global__ void __launch_bounds__(32)
+permute_bulk_kernel(PermuteArgs a, const int32_t* __restrict__ row_src, const int32_t* __restrict__ n_rows_dev,
+                    int cap, long long chunks_per_rowset) {
+    extern __shared__ __align__(128) unsigned char sbuf[];
+    __shared__ __align__(8) uint64_t full[kBulkStages];
+    const int R = min(*n_rows_dev, cap);
+    const long long total = (long long)cap * chunks_per_rowset;
+    if (threadIdx.x != 0) return;
+    for (int s = 0; s < kBulkStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    // software pipeline over this CTA's items k = 0..n-1 (global item = blockIdx.x + k*gridDim.x):
+    // loads run kLookahead items ahead of the stores; the buffer a load reuses was last read by store
+    // k-2, i.e. everything but the most recent bulk group must have finished reading shared memory.
+    constexpr int kLookahead = kBulkStages - 2;
+    const long long n = total > blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto decode = [&](long long k, const char*& src, char*& dst, uint32_t& bytes) {
+        const long long item = blockIdx.x + k * (long long)gridDim.x;
+        const int r = (int)(item / chunks_per_rowset);
+        long long c = item - (long long)r * chunks_per_rowset;
+        int i = 0;
+        while (i + 1 < a.n_tensors && c >= a.chunk_base[i + 1]) ++i;
+        c -= a.chunk_base[i];
+        const long long off = c * kChunk;
+        const long long rem = a.row_bytes[i] - off;
+        bytes = (uint32_t)(rem < kChunk ? rem : kChunk);
+        dst = a.dst[i] + (long long)r * a.row_bytes[i] + off;
+        src = r < R ? a.src[i] + (long long)row_src[r] * a.row_bytes[i] + off : nullptr;   // tail rows: zero-fill
+    };
+    auto load = [&](long long k) {
+        const int s = (int)(k % kBulkStages);
+        const char* src;
+        char* dst;
+        uint32_t bytes;
+        decode(k, src, dst, bytes);
+        if (src) {
+            mbar_expect_tx(&full[s], bytes);
+            bulk_g2s(sbuf + (size_t)s * kChunk, src, bytes, &full[s]);
+        } else {
+            int4* z = reinterpret_cast<int4*>(sbuf + (size_t)s * kChunk);
+            for (uint32_t q = 0; q < bytes / 16; ++q) z[q] = make_int4(0, 0, 0, 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&full[s], 0);
+        }
+    };
+    for (long long k = 0; k < kLookahead && k < n; ++k) load(k);
+    for (long long k = 0; k < n; ++k) {
+        if (k + kLookahead < n) {
+            if (k >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            load(k + kLookahead);
+        }
+        const int s = (int)(k % kBulkStages);
+        const char* src;
+        char* dst;
+        uint32_t bytes;
+        decode(k, src, dst, bytes);
+        mbar_wait(&full[s], (uint32_t)((k / kBulkStages) & 1));
+        bulk_s2g(dst, sbuf + (size_t)s * kChunk, bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// vector path: one warp per (row, tensor, 2 KiB piece)
+constexpr int kVecPiece = 2048;
+__global__ void __launch_bounds__(256)
+permute_vec_kernel(PermuteArgs a, const int32_t* __restrict__ row_src, const int32_t* __restrict__ n_rows_dev,
+                   int cap, long long pieces_per_rowset, long long piece_base1, long long piece_base2,
+                   long long piece_base3) {
+    const int R = min(*n_rows_dev, cap);
+    const long long total = (long long)cap * pieces_per_rowset;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long item = warp0; item < total; item += nwarps) {
+        const int r = (int)(item / pieces_per_rowset);
+        long long c = item - (long long)r * pieces_per_rowset;
+        int i = 0;
+        if (a.n_tensors > 3 && c >= piece_base3) { i = 3; c -= piece_base3; }
+        else if (a.n_tensors > 2 && c >= piece_base2) { i = 2; c -= piece_base2; }
+        else if (a.n_tensors > 1 && c >= piece_base1) { i = 1; c -= piece_base1; }
+        const long long off = c * kVecPiece;
+        const long long rem = a.row_bytes[i] - off;
+        const int bytes = (int)(rem < kVecPiece ? rem : kVecPiece);
+        char* dst = a.dst[i] + (long long)r * a.row_bytes[i] + off;
+        const bool live = r < R;
+        const char* src = live ? a.src[i] + (long long)row_src[r] * a.row_bytes[i] + off : nullptr;
+        const bool al16 = ((((uintptr_t)dst) | ((uintptr_t)(live ? src : dst)) | (uintptr_t)bytes) & 15) == 0;
+        if (al16) {
+            const int n16 = bytes >> 4;
+            int4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = lane + 32 * q;
+                v[q] = (live && j < n16) ? ld_stream(reinterpret_cast<const int4*>(src) + j) : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = lane + 32 * q;
+                if (j < n16) st_stream(reinterpret_cast<int4*>(dst) + j, v[q]);
+            }
+        } else {
+            const int n4 = bytes >> 2;
+            for (int j = lane; j < n4; j += 32)
+                reinterpret_cast<int*>(dst)[j] = live ? reinterpret_cast<const int*>(src)[j] : 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Combine.  grid-stride over (token, 4-element vector); K <= 8 gathered rows per token.
+// ---------------------------------------------------------------------------------------------------
+template <typename TR, typename TO>
+__global__ void __launch_bounds__(256)
+combine_kernel(const TR* __restrict__ rows, const int32_t* __restrict__ tok_rows, const float* __restrict__ row_w,
+               const TO* __restrict__ base, TO* __restrict__ out, int T, int K, long long D) {
+    const long long vec_per_row = D >> 2;
+    const long long total = (long long)T * vec_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / vec_per_row);
+        const long long d = (i - (long long)t * vec_per_row) << 2;
+        float4 acc = base ? Vec4<TO>::load(base + (long long)t * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < K; ++j) {
+            const int r = tok_rows[(long long)t * K + j];
+            if (r < 0) continue;
+            const float w = row_w ? row_w[r] : 1.f;
+            const float4 v = Vec4<TR>::load(rows + (long long)r * D + d);
+            // multiply, round, then add (the reference does `out_e * w` then `+=`): no FMA contraction
+            acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, w));
+            acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, w));
+            acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, w));
+            acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, w));
+        }
+        Vec4<TO>::store(out + (long long)t * D + d, acc);
+    }
+}
+
+// backward: one CTA per permuted row.  d_rows[r] = w_r * dY[src_r];  d_sparse[src_r, e_r] = <rows[r], dY[src_r]>
+template <typename TR, typename TY>
+__global__ void __launch_bounds__(256)
+combine_bwd_kernel(const TR* __restrict__ rows, const TY* __restrict__ dY, const int32_t* __restrict__ row_src,
+                   const int32_t* __restrict__ row_expert, const float* __restrict__ row_w,
+                   const int32_t* __restrict__ n_rows_dev, int cap, int E, long long D, TR* __restrict__ d_rows,
+                   float* __restrict__ d_sparse_w) {
+    __shared__ float red[8];
+    const int R = min(*n_rows_dev, cap);
+    for (int r = blockIdx.x; r < cap; r += gridDim.x) {
+        TR* dr = d_rows + (long long)r * D;
+        if (r >= R) {
+            for (long long d = (long long)threadIdx.x << 2; d < D; d += (long long)blockDim.x << 2)
+                Vec4<TR>::store(dr + d, make_float4(0.f, 0.f, 0.f, 0.f));
+            continue;
+        }
+        const int t = row_src[r];
+        const float w = row_w ? row_w[r] : 1.f;
+        const TY* gy = dY + (long long)t * D;
+        const TR* xr = rows ? rows + (long long)r * D : nullptr;
+        float dot = 0.f;
+        for (long long d = (long long)threadIdx.x << 2; d < D; d += (long long)blockDim.x << 2) {
+            const float4 g = Vec4<TY>::load(gy + d);
+            Vec4<TR>::store(dr + d, make_float4(g.x * w, g.y * w, g.z * w, g.w * w));
+            if (xr) {
+                const float4 x = Vec4<TR>::load(xr + d);
+                dot += g.x * x.x + g.y * x.y + g.z * x.z + g.w * x.w;
+            }
+        }
+        if (d_sparse_w) {
+            dot = warp_sum(dot);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float s = 0.f;
+                for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += red[q];
+                d_sparse_w[(long long)t * E + row_expert[r]] = s;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace hdmoe
+
+using namespace hdmoe;
+
+extern "C" size_t hdmoe_dispatch_plan_workspace_bytes(int T, int E) {
+    const size_t ntiles = (size_t)(T + kPlanThreads - 1) / kPlanThreads + 1;
+    return 2 * ntiles * (size_t)E * sizeof(int32_t) + 64;
+}
+
+extern "C" int hdmoe_dispatch_plan(const float* sparse_w, int T, int E, int cap, int K, int32_t* counts,
+                                   int32_t* offsets, int32_t* row_src, int32_t* row_expert, float* row_w,
+                                   int32_t* tok_rows, int32_t* status, void* workspace, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(T >= 1 && E >= 1 && E <= HDMOE_MAX_EXPERTS, "dispatch_plan: need T >= 1, 1 <= E <= %d",
+                    HDMOE_MAX_EXPERTS);
+    HDMOE_CHECK_ARG(cap >= 1 && K >= 1 && K <= E, "dispatch_plan: need cap >= 1 and 1 <= K <= E");
+    HDMOE_CHECK_ARG(sparse_w && counts && offsets && row_src && row_expert && row_w && tok_rows && status && workspace,
+                    "dispatch_plan: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ntiles = (T + kPlanThreads - 1) / kPlanThreads;
+    int32_t* tilecnt = (int32_t*)workspace;
+    int32_t* tileoff = tilecnt + (size_t)E * ntiles;
+    plan_count_kernel<<<ntiles, kPlanThreads, 0, st>>>(sparse_w, T, E, ntiles, tilecnt);
+    HDMOE_CHECK_LAUNCH();
+    plan_scan_kernel<<<1, 1024, 0, st>>>(tilecnt, E, ntiles, cap, tileoff, counts, offsets, status);
+    HDMOE_CHECK_LAUNCH();
+    plan_scatter_kernel<<<ntiles, kPlanThreads, 0, st>>>(sparse_w, T, E, ntiles, cap, K, tileoff, row_src, row_expert,
+                                                         row_w, tok_rows, status);
+    HDMOE_CHECK_LAUNCH();
+    plan_tail_kernel<<<grid_for(cap, 256, 2), 256, 0, st>>>(offsets, E, cap, row_src, row_expert, row_w);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_permute_rows(const void* const* srcs, void* const* dsts, const int64_t* row_bytes, int n_tensors,
+                                  const int32_t* row_src, const int32_t* n_rows_dev, int cap, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(n_tensors >= 1 && n_tensors <= 4, "permute_rows: 1..4 tensors per call");
+    HDMOE_CHECK_ARG(row_src && n_rows_dev && cap >= 1, "permute_rows: null index / cap < 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    PermuteArgs a{};
+    a.n_tensors = n_tensors;
+    bool bulk_ok = true;
+    long long max_row = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+        HDMOE_CHECK_ARG(srcs[i] && dsts[i] && row_bytes[i] > 0 && row_bytes[i] % 4 == 0,
+                        "permute_rows: tensor %d: null pointer or row_bytes %% 4 != 0", i);
+        a.src[i] = (const char*)srcs[i];
+        a.dst[i] = (char*)dsts[i];
+        a.row_bytes[i] = row_bytes[i];
+        if (row_bytes[i] % 16 || ((uintptr_t)srcs[i] & 15) || ((uintptr_t)dsts[i] & 15)) bulk_ok = false;
+        if (row_bytes[i] > max_row) max_row = row_bytes[i];
+    }
+    if (bulk_ok && max_row >= 4096) {
+        long long base = 0;
+        for (int i = 0; i < n_tensors; ++i) {
+            a.chunk_base[i] = base;
+            a.chunks_per_row[i] = (row_bytes[i] + kChunk - 1) / kChunk;
+            base += a.chunks_per_row[i];
+        }
+        const long long total = (long long)cap * base;
+        const int smem = kBulkStages * kChunk;
+        static bool attr_set = false;
+        if (!attr_set) {
+            HDMOE_CHECK_CUDA(cudaFuncSetAttribute(permute_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
+        }
+        long long g = total < (long long)kNumSMs * 2 ? total : (long long)kNumSMs * 2;
+        permute_bulk_kernel<<<(int)g, 32, smem, st>>>(a, row_src, n_rows_dev, cap, base);
+        HDMOE_CHECK_LAUNCH();
+    } else {
+        long long pb[4] = {0, 0, 0, 0}, base = 0;
+        for (int i = 0; i < n_tensors; ++i) {
+            pb[i] = base;
+            base += (row_bytes[i] + kVecPiece - 1) / kVecPiece;
+        }
+        const long long total = (long long)cap * base;
+        permute_vec_kernel<<<grid_for(total, 8, 16), 256, 0, st>>>(a, row_src, n_rows_dev, cap, base, pb[1], pb[2], pb[3]);
+        HDMOE_CHECK_LAUNCH();
+    }
+    return HDMOE_OK;
+}
+
+template <typename TR, typename TO>
+static int launch_combine(const void* rows, const int32_t* tok_rows, const float* row_w, const void* base, void* out,
+                          int T, int K, int64_t D, cudaStream_t st) {
+    const long long total = (long long)T * (D >> 2);
+    combine_kernel<TR, TO><<<grid_for(total, 256, 16), 256, 0, st>>>((const TR*)rows, tok_rows, row_w, (const TO*)base,
+                                                                    (TO*)out, T, K, D);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_combine_rows(const void* rows, int rows_dtype, const int32_t* tok_rows, const float* row_w,
+                                  const void* base, void* out, int out_dtype, int T, int K, int64_t D,
+                                  hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(rows && tok_rows && out && T >= 1 && K >= 1 && K <= HDMOE_MAX_EXPERTS, "combine_rows: bad args");
+    HDMOE_CHECK_ARG(D >= 4 && D % 4 == 0, "combine_rows: row width must be a multiple of 4 elements (got %lld)",
+                    (long long)D);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows_dtype == HDMOE_F32 && out_dtype == HDMOE_F32)
+        return launch_combine<float, float>(rows, tok_rows, row_w, base, out, T, K, D, st);
+    if (rows_dtype == HDMOE_BF16 && out_dtype == HDMOE_BF16)
+        return launch_combine<__nv_bfloat16, __nv_bfloat16>(rows, tok_rows, row_w, base, out, T, K, D, st);
+    if (rows_dtype == HDMOE_BF16 && out_dtype == HDMOE_F32)
+        return launch_combine<__nv_bfloat16, float>(rows, tok_rows, row_w, base, out, T, K, D, st);
+    if (rows_dtype == HDMOE_F32 && out_dtype == HDMOE_BF16)
+        return launch_combine<float, __nv_bfloat16>(rows, tok_rows, row_w, base, out, T, K, D, st);
+    HDMOE_CHECK_ARG(false, "combine_rows: unsupported dtype pair (%d, %d)", rows_dtype, out_dtype);
+}
+
+template <typename TR, typename TY>
+static int launch_combine_bwd(const void* rows, const void* dY, const int32_t* row_src, const int32_t* row_expert,
+                              const float* row_w, const int32_t* n_rows_dev, int cap, int E, int64_t D, void* d_rows,
+                              float* d_sparse_w, cudaStream_t st) {
+    int grid = cap < kNumSMs * 8 ? cap : kNumSMs * 8;
+    combine_bwd_kernel<TR, TY><<<grid, 256, 0, st>>>((const TR*)rows, (const TY*)dY, row_src, row_expert, row_w,
+                                                     n_rows_dev, cap, E, D, (TR*)d_rows, d_sparse_w);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_combine_rows_bwd(const void* rows, int rows_dtype, const void* dY, int dy_dtype,
+                                      const int32_t* row_src, const int32_t* row_expert, const float* row_w,
+                                      const int32_t* n_rows_dev, int cap, int T, int E, int64_t D, void* d_rows,
+                                      float* d_sparse_w, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(dY && row_src && row_expert && n_rows_dev && d_rows && cap >= 1, "combine_rows_bwd: bad args");
+    HDMOE_CHECK_ARG(D >= 4 && D % 4 == 0, "combine_rows_bwd: row width must be a multiple of 4 elements");
+    HDMOE_CHECK_ARG(!d_sparse_w || rows, "combine_rows_bwd: d_sparse_w needs the forward rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_sparse_w) HDMOE_CHECK_CUDA(cudaMemsetAsync(d_sparse_w, 0, (size_t)T * E * sizeof(float), st));
+    if (rows_dtype == HDMOE_F32 && dy_dtype == HDMOE_F32)
+        return launch_combine_bwd<float, float>(rows, dY, row_src, row_expert, row_w, n_rows_dev, cap, E, D, d_rows,
+                                                d_sparse_w, st);
+    if (rows_dtype == HDMOE_BF16 && dy_dtype == HDMOE_BF16)
+        return launch_combine_bwd<__nv_bfloat16, __nv_bfloat16>(rows, dY, row_src, row_expert, row_w, n_rows_dev, cap,
+                                                                E, D, d_rows, d_sparse_w, st);
+    if (rows_dtype == HDMOE_BF16 && dy_dtype == HDMOE_F32)
+        return launch_combine_bwd<__nv_bfloat16, float>(rows, dY, row_src, row_expert, row_w, n_rows_dev, cap, E, D,
+                                                        d_rows, d_sparse_w, st);
+    if (rows_dtype == HDMOE_F32 && dy_dtype == HDMOE_BF16)
+        return launch_combine_bwd<float, __nv_bfloat16>(rows, dY, row_src, row_expert, row_w, n_rows_dev, cap, E, D,
+                                                        d_rows, d_sparse_w, st);
+    HDMOE_CHECK_ARG(false, "combine_rows_bwd: unsupported dtype pair");
+}

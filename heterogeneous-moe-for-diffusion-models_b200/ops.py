@@ -1,0 +1,426 @@
+"""torch.autograd bindings of the sm_100a kernels (C ABI in include/hdmoe_b200.h).
+
+Every function here launches hand-written CUDA through ctypes on torch's current stream.  There is no
+CPU / eager fallback: non-CUDA tensors raise.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"hdmoe_b200: unsupported dtype {t.dtype} (float32 / bfloat16 only)") from None
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hdmoe_b200 kernels need CUDA tensors; there is no CPU fallback")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+_ws_cache = {}
+
+
+def _zero_workspace(nbytes: int, device) -> torch.Tensor:
+    """Persistent zero-initialised workspace (the kernels leave it zeroed again)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+# ----------------------------------------------------------------------------------------------------
+# (1) router gate
+# ----------------------------------------------------------------------------------------------------
+class _RouterGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pooled, cond, w_hat, noise, zeta, mask, logits_in, top_k):
+        lib = L.lib()
+        src = logits_in if logits_in is not None else pooled
+        _cuda(src, cond, w_hat, noise, mask)
+        T = src.shape[0]
+        if logits_in is not None:
+            E, Cc = logits_in.shape[1], 0
+            logits_in = _f32c(logits_in)
+        else:
+            pooled, w_hat, cond = _f32c(pooled), _f32c(w_hat), _f32c(cond)
+            E, Cc = w_hat.shape
+            assert pooled.shape == (T, Cc) and (cond is None or cond.shape == (T, 2 * Cc))
+        noise, mask = _f32c(noise), _f32c(mask)
+        dev = src.device
+        o = dict(dtype=torch.float32, device=dev)
+        logits, probs, sparse = (torch.empty(T, E, **o) for _ in range(3))
+        idx = torch.empty(T, top_k, dtype=torch.int32, device=dev)
+        tw = torch.empty(T, top_k, **o)
+        stats = torch.empty(2 * E + 1, **o)
+        ws = _zero_workspace(lib.hdmoe_router_gate_workspace_bytes(T, E), dev)
+        L.check(lib.hdmoe_router_gate_fwd(_p(pooled), _p(cond), _p(w_hat), _p(noise), float(zeta), _p(mask),
+                                          _p(logits_in), T, Cc, E, top_k, _p(logits), _p(probs), _p(sparse),
+                                          _p(idx), _p(tw), _p(stats), _p(ws), _st()), "router_gate_fwd")
+        ctx.save_for_backward(pooled, cond, w_hat, logits, idx)
+        ctx.dims = (T, Cc, E, top_k, logits_in is not None)
+        ctx.mark_non_differentiable(idx, tw)
+        return sparse, probs, logits, idx, tw, stats
+
+    @staticmethod
+    def backward(ctx, g_sparse, g_probs, g_logits, _gi, _gw, g_stats):
+        pooled, cond, w_hat, logits, idx = ctx.saved_tensors
+        T, Cc, E, k, teacher = ctx.dims
+        lib = L.lib()
+        g_sparse, g_probs, g_logits, g_stats = (_f32c(g) for g in (g_sparse, g_probs, g_logits, g_stats))
+        if teacher:
+            d_logits = torch.empty_like(logits)
+            L.check(lib.hdmoe_router_gate_bwd(None, None, None, _p(logits), _p(idx), _p(g_sparse), _p(g_probs),
+                                              _p(g_logits), _p(g_stats), T, 0, E, k, None, None, None,
+                                              _p(d_logits), _st()), "router_gate_bwd")
+            return None, None, None, None, None, None, d_logits, None
+        d_pooled = torch.empty_like(pooled)
+        d_cond = torch.empty_like(cond) if cond is not None else None
+        d_w = torch.empty_like(w_hat)
+        L.check(lib.hdmoe_router_gate_bwd(_p(pooled), _p(cond), _p(w_hat), _p(logits), _p(idx), _p(g_sparse),
+                                          _p(g_probs), _p(g_logits), _p(g_stats), T, Cc, E, k, _p(d_pooled),
+                                          _p(d_cond), _p(d_w), None, _st()), "router_gate_bwd")
+        return d_pooled, d_cond, d_w, None, None, None, None, None
+
+
+def router_gate(pooled, cond, w_hat, top_k: int, noise=None, zeta: float = 0.0, mask=None):
+    """Fused router tail.  Returns (sparse_w, gate_probs, logits, topk_idx[int32], topk_w, stats);
+    stats = [sum_t probs (E) | dispatch counts (E) | sum_t z-term (1)].  See include/hdmoe_b200.h §1."""
+    return _RouterGate.apply(pooled, cond, w_hat, noise, zeta, mask, None, top_k)
+
+
+def router_gate_from_logits(logits, top_k: int, mask=None):
+    """Teacher-forced gate on given (already masked) logits: bit-exact index contract."""
+    return _RouterGate.apply(None, None, None, None, 0.0, mask, logits, top_k)
+
+
+# ----------------------------------------------------------------------------------------------------
+# (2) dispatch plan, permute
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class DispatchPlan:
+    """Integer dispatch plan (device tensors; see include/hdmoe_b200.h §2)."""
+    T: int
+    E: int
+    K: int
+    cap: int
+    counts: torch.Tensor
+    offsets: torch.Tensor
+    row_src: torch.Tensor
+    row_expert: torch.Tensor
+    row_w: torch.Tensor
+    tok_rows: torch.Tensor
+    status: torch.Tensor
+    _host_offsets: Optional[List[int]] = None
+
+    @property
+    def n_rows_dev(self) -> torch.Tensor:
+        return self.offsets[self.E:self.E + 1]
+
+    def host_offsets(self) -> List[int]:
+        """offsets as python ints -- ONE device->host copy (the reference syncs >= 2E times per layer)."""
+        if self._host_offsets is None:
+            both = torch.cat([self.offsets, self.status]).tolist()
+            if both[-1] != 0:
+                raise RuntimeError(f"dispatch plan overflow (status {both[-1]}): cap={self.cap}, K={self.K}")
+            self._host_offsets = both[:-1]
+        return self._host_offsets
+
+
+def dispatch_plan(sparse_w: torch.Tensor, top_k: Optional[int] = None) -> DispatchPlan:
+    """Expert-major, token-ascending dispatch plan of the entries with sparse_w > 0 (bit-exact)."""
+    _cuda(sparse_w)
+    lib = L.lib()
+    w = _f32c(sparse_w.detach())
+    T, E = w.shape
+    K = E if top_k is None else min(int(top_k), E)
+    cap = T * K
+    dev = w.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    counts, offsets = torch.empty(E, **i32), torch.empty(E + 1, **i32)
+    row_src, row_expert = torch.empty(cap, **i32), torch.empty(cap, **i32)
+    row_w = torch.empty(cap, dtype=torch.float32, device=dev)
+    tok_rows = torch.empty(T, K, **i32)
+    status = torch.empty(1, **i32)
+    ws = torch.empty(lib.hdmoe_dispatch_plan_workspace_bytes(T, E), dtype=torch.uint8, device=dev)
+    L.check(lib.hdmoe_dispatch_plan(_p(w), T, E, cap, K, _p(counts), _p(offsets), _p(row_src), _p(row_expert),
+                                    _p(row_w), _p(tok_rows), _p(status), _p(ws), _st()), "dispatch_plan")
+    return DispatchPlan(T, E, K, cap, counts, offsets, row_src, row_expert, row_w, tok_rows, status)
+
+
+def _permute_raw(srcs: Sequence[torch.Tensor], plan: DispatchPlan) -> List[torch.Tensor]:
+    lib = L.lib()
+    outs, n = [], len(srcs)
+    for lo in range(0, n, 4):
+        grp = [s.contiguous() for s in srcs[lo:lo + 4]]
+        dst = [torch.empty((plan.cap,) + tuple(s.shape[1:]), dtype=s.dtype, device=s.device) for s in grp]
+        m = len(grp)
+        a_src = (C.c_void_p * m)(*[s.data_ptr() for s in grp])
+        a_dst = (C.c_void_p * m)(*[d.data_ptr() for d in dst])
+        a_rb = (C.c_int64 * m)(*[s[0].numel() * s.element_size() for s in grp])
+        L.check(lib.hdmoe_permute_rows(a_src, a_dst, a_rb, m, _p(plan.row_src), _p(plan.n_rows_dev), plan.cap,
+                                       _st()), "permute_rows")
+        outs += dst
+    return outs
+
+
+def _combine_raw(rows, tok_rows, row_w, base, out_dtype, T, K):
+    lib = L.lib()
+    rows = rows.contiguous()
+    D = rows[0].numel()
+    out = torch.empty((T,) + tuple(rows.shape[1:]), dtype=out_dtype, device=rows.device)
+    if base is not None:
+        base = base.to(out_dtype).contiguous()
+    L.check(lib.hdmoe_combine_rows(_p(rows), _dt(rows), _p(tok_rows), _p(row_w), _p(base), _p(out), _dt(out),
+                                   T, K, D, _st()), "combine_rows")
+    return out
+
+
+class _Permute(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, *srcs):
+        _cuda(*srcs)
+        for s in srcs:
+            if s.shape[0] != plan.T:
+                raise RuntimeError(f"permute: leading dim {s.shape[0]} != plan.T {plan.T}")
+        ctx.plan = plan
+        return tuple(_permute_raw(srcs, plan))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        plan = ctx.plan
+        out = []
+        for g in grads:
+            # d_src[t] = sum_j d_rows[tok_rows[t, j]]: the combine kernel with unit weights
+            out.append(None if g is None else _combine_raw(g, plan.tok_rows, None, None, g.dtype, plan.T, plan.K))
+        return (None, *out)
+
+
+def permute(plan: DispatchPlan, *srcs: torch.Tensor):
+    """Gather rows of every `src` ([T, ...]) into expert-major order -> [cap, ...] (tail rows zero)."""
+    return _Permute.apply(plan, *srcs)
+
+
+# ----------------------------------------------------------------------------------------------------
+# (3) combine
+# ----------------------------------------------------------------------------------------------------
+class _Combine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, sparse_w, base, plan, out_dtype):
+        _cuda(rows, sparse_w, base)
+        ctx.plan = plan
+        ctx.has_base = base is not None
+        ctx.need_w = ctx.needs_input_grad[1]
+        ctx.save_for_backward(rows if ctx.need_w else None)
+        ctx.rows_meta = (rows.dtype, tuple(rows.shape))
+        return _combine_raw(rows, plan.tok_rows, plan.row_w, base, out_dtype, plan.T, plan.K)
+
+    @staticmethod
+    def backward(ctx, dY):
+        plan = ctx.plan
+        (rows,) = ctx.saved_tensors
+        lib = L.lib()
+        dY = dY.contiguous()
+        rdt, rshape = ctx.rows_meta
+        d_rows = torch.empty(rshape, dtype=rdt, device=dY.device)
+        d_sparse = torch.empty(plan.T, plan.E, dtype=torch.float32, device=dY.device) if ctx.need_w else None
+        D = dY[0].numel()
+        L.check(lib.hdmoe_combine_rows_bwd(_p(rows), _DT[rdt], _p(dY), _dt(dY), _p(plan.row_src),
+                                           _p(plan.row_expert), _p(plan.row_w), _p(plan.n_rows_dev), plan.cap,
+                                           plan.T, plan.E, D, _p(d_rows), _p(d_sparse), _st()), "combine_rows_bwd")
+        return d_rows, d_sparse, (dY if ctx.has_base else None), None, None
+
+
+def combine(rows: torch.Tensor, sparse_w: torch.Tensor, plan: DispatchPlan, base: Optional[torch.Tensor] = None,
+            out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """out[t] = (base[t]) + sum over dispatched experts (ascending) of sparse_w[t, e] * rows[row(t, e)]."""
+    return _Combine.apply(rows, sparse_w, base, plan, out_dtype or rows.dtype)
+
+
+# ----------------------------------------------------------------------------------------------------
+# (4) EDM preconditioning / Heun step
+# ----------------------------------------------------------------------------------------------------
+def _sigma_vec(sigma: torch.Tensor, B: int) -> torch.Tensor:
+    s = sigma.detach().to(torch.float32).reshape(-1).contiguous()
+    if s.numel() not in (1, B):
+        raise RuntimeError(f"sigma has {s.numel()} elements, expected 1 or batch size {B}")
+    return s
+
+
+class _PrecondIn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, sigma, sigma_data, out_dtype):
+        _cuda(x, sigma)
+        x = _f32c(x)
+        B, per = x.shape[0], x[0].numel()
+        s = _sigma_vec(sigma, B)
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        L.check(L.lib().hdmoe_edm_precond_in(_p(x), _p(s), s.numel(), float(sigma_data), _p(out), _dt(out), B, per,
+                                             _st()), "edm_precond_in")
+        ctx.save_for_backward(s)
+        ctx.sd = float(sigma_data)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (s,) = ctx.saved_tensors
+        g = g.contiguous()
+        B, per = g.shape[0], g[0].numel()
+        dx = torch.empty(g.shape, dtype=torch.float32, device=g.device)
+        L.check(L.lib().hdmoe_edm_precond_in_bwd(_p(g), _dt(g), _p(s), s.numel(), ctx.sd, _p(dx), B, per, _st()),
+                "edm_precond_in_bwd")
+        return dx, None, None, None
+
+
+class _PrecondOut(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_in, F, sigma, sigma_data):
+        _cuda(x_in, F, sigma)
+        x_in, F = x_in.contiguous(), F.contiguous()
+        B, per = x_in.shape[0], x_in[0].numel()
+        s = _sigma_vec(sigma, B)
+        D = torch.empty(x_in.shape, dtype=torch.float32, device=x_in.device)
+        L.check(L.lib().hdmoe_edm_precond_out(_p(x_in), _dt(x_in), _p(F), _dt(F), _p(s), s.numel(), float(sigma_data),
+                                              _p(D), B, per, _st()), "edm_precond_out")
+        ctx.save_for_backward(s)
+        ctx.meta = (float(sigma_data), x_in.dtype, F.dtype)
+        return D
+
+    @staticmethod
+    def backward(ctx, g):
+        (s,) = ctx.saved_tensors
+        sd, xdt, fdt = ctx.meta
+        g = _f32c(g)
+        B, per = g.shape[0], g[0].numel()
+        dF = torch.empty(g.shape, dtype=fdt, device=g.device)
+        dX = torch.empty(g.shape, dtype=xdt, device=g.device)
+        L.check(L.lib().hdmoe_edm_precond_out_bwd(_p(g), _p(s), s.numel(), sd, _p(dF), _DT[fdt], _p(dX), _DT[xdt], B,
+                                                  per, _st()), "edm_precond_out_bwd")
+        return dX, dF, None, None
+
+
+def edm_precond_in(x, sigma, sigma_data: float, out_dtype=torch.float32):
+    """x * c_in(sigma)  (models/model_config2.py:434,440)."""
+    return _PrecondIn.apply(x, sigma, sigma_data, out_dtype)
+
+
+def edm_precond_out(x_in, F, sigma, sigma_data: float):
+    """c_skip * x_in + c_out * F  (models/model_config2.py:449, with quirk Q1)."""
+    return _PrecondOut.apply(x_in, F, sigma, sigma_data)
+
+
+def edm_heun_pre(x_cur, eps, noise_scale: float, t_hat: float, sigma_data: float, x_in_dtype=torch.float32):
+    _cuda(x_cur, eps)
+    x_cur = _f32c(x_cur)
+    eps = _f32c(eps) if (eps is not None and noise_scale != 0.0) else None
+    x_hat = torch.empty_like(x_cur)
+    x_in = torch.empty(x_cur.shape, dtype=x_in_dtype, device=x_cur.device)
+    L.check(L.lib().hdmoe_edm_heun_pre(_p(x_cur), _p(eps), float(noise_scale), float(t_hat), float(sigma_data),
+                                       _p(x_hat), _p(x_in), _dt(x_in), x_cur.numel(), _st()), "edm_heun_pre")
+    return x_hat, x_in
+
+
+def edm_heun_euler(x_hat, x_in, F, F_guide, guidance: float, t_hat: float, t_next: float, sigma_data: float):
+    _cuda(x_hat, x_in, F, F_guide)
+    F = F.contiguous()
+    F_guide = None if F_guide is None else F_guide.to(F.dtype).contiguous()
+    d_cur, x_next = torch.empty_like(x_hat), torch.empty_like(x_hat)
+    x_in_next = torch.empty_like(x_in) if (t_next > 0 and x_in is not None) else None
+    L.check(L.lib().hdmoe_edm_heun_euler(_p(x_hat), _p(x_in), _dt(x_in) if x_in is not None else L.F32, _p(F), _p(F_guide), _dt(F), float(guidance),
+                                         float(t_hat), float(t_next), float(sigma_data), _p(d_cur), _p(x_next),
+                                         _p(x_in_next), x_hat.numel(), _st()), "edm_heun_euler")
+    return d_cur, x_next, x_in_next
+
+
+def edm_heun_correct(x_hat, x_next, x_in_next, F, F_guide, guidance: float, t_hat: float, t_next: float,
+                     sigma_data: float, d_cur):
+    _cuda(x_hat, x_next, x_in_next, F, F_guide, d_cur)
+    F = F.contiguous()
+    F_guide = None if F_guide is None else F_guide.to(F.dtype).contiguous()
+    out = torch.empty_like(x_hat)
+    L.check(L.lib().hdmoe_edm_heun_correct(_p(x_hat), _p(x_next), _p(x_in_next),
+                                           _dt(x_in_next) if x_in_next is not None else L.F32, _p(F), _p(F_guide),
+                                           _dt(F), float(guidance), float(t_hat), float(t_next), float(sigma_data),
+                                           _p(d_cur), _p(out), x_hat.numel(), _st()), "edm_heun_correct")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# (5) W-PREP
+# ----------------------------------------------------------------------------------------------------
+class WeightPrep:
+    """Multi-tensor weight preparation plan: one launch normalises / scales / casts many MP_Conv weights."""
+
+    def __init__(self, entries, device):
+        """entries: list of dicts {w: Parameter [rows, ...], out: Tensor, gain: float | Tensor,
+        layout: 'same' | 'taps', cin_pad: int}"""
+        self.n = len(entries)
+        self.entries = entries
+        self.descs = (L.WprepDesc * self.n)()
+        self.dev_buf = torch.empty(self.n * C.sizeof(L.WprepDesc), dtype=torch.uint8, device=device)
+        self._fill()
+
+    def _fill(self):
+        for d, e in zip(self.descs, self.entries):
+            w, out = e["w"], e["out"]
+            assert w.dtype == torch.float32 and w.is_contiguous() and w.is_cuda
+            rows = w.shape[0]
+            fan_in = w[0].numel()
+            taps = 1
+            for s in w.shape[2:]:
+                taps *= s
+            cin = fan_in // taps
+            g = e.get("gain", 1.0)
+            d.w, d.w_hat = w.data_ptr(), out.data_ptr()
+            if torch.is_tensor(g):
+                d.gain_ptr, d.gain = g.data_ptr(), 0.0
+            else:
+                d.gain_ptr, d.gain = None, float(g)
+            d.rows, d.fan_in, d.cin, d.taps = rows, fan_in, cin, taps
+            d.cin_pad = int(e.get("cin_pad", cin))
+            d.out_dtype = _dt(out)
+            d.layout = L.WLAYOUT_TAPS if e.get("layout", "same") == "taps" else L.WLAYOUT_SAME
+
+    def run(self, force: bool):
+        self._fill()      # pointers may have moved (optimizer swaps, .to())
+        L.check(L.lib().hdmoe_wprep_fwd(self.descs, _p(self.dev_buf), self.n, int(bool(force)), _st()), "wprep_fwd")
+
+
+def wprep_bwd(w, d_w_hat, gain):
+    """d_w (and d_gain when gain is a tensor) from d_w_hat through one normalisation."""
+    _cuda(w, d_w_hat)
+    w2 = w.detach().reshape(w.shape[0], -1).contiguous()
+    g2 = _f32c(d_w_hat.reshape(w.shape[0], -1))
+    d_w = torch.empty_like(w2)
+    gt = gain if torch.is_tensor(gain) else None
+    d_gain = torch.zeros((), dtype=torch.float32, device=w.device) if gt is not None else None
+    L.check(L.lib().hdmoe_wprep_bwd(_p(w2), _p(g2), _p(gt), 0.0 if gt is not None else float(gain), w2.shape[0],
+                                    w2.shape[1], _p(d_w), _p(d_gain), _st()), "wprep_bwd")
+    return d_w.reshape(w.shape), d_gain

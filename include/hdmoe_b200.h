@@ -1,0 +1,194 @@
+/*
+ * hdmoe_b200.h -- C ABI of libhdmoe_b200.so (hand-written sm_100a kernels for the heterogeneous-MoE
+ * hot path of the EDM denoiser).
+ *
+ * The reference (cs2mosa/Heterogeneous-MOE-for-Diffusion-models) is 100 % Python/PyTorch and has no
+ * FFI of its own; the drop-in boundary is its nn.Module surface, which the Python
+ * package next to this header mirrors.  This header is the boundary *below* those modules: each entry
+ * point replaces the chain of ATen calls the cited reference lines launch.  All `file:line` citations
+ * are relative to the reference repository root.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless it says "host";
+ *   - no allocation inside: outputs and workspaces are caller-provided;
+ *   - kernels are enqueued on `stream` (a cudaStream_t); nothing synchronises the host;
+ *   - return 0 on success, a negative HDMOE_ERR_* otherwise; hdmoe_last_error() gives the text;
+ *   - dtype codes: HDMOE_F32 = 0, HDMOE_BF16 = 1.
+ */
+#ifndef HDMOE_B200_H_
+#define HDMOE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hdmoe_stream_t; /* cudaStream_t */
+
+#define HDMOE_F32 0
+#define HDMOE_BF16 1
+
+#define HDMOE_OK 0
+#define HDMOE_ERR_ARG (-1)      /* bad argument (shape / alignment / unsupported size)     */
+#define HDMOE_ERR_CUDA (-2)     /* a CUDA runtime / driver call failed                      */
+#define HDMOE_ERR_NO_DEVICE (-3)/* no sm_100 device present                                 */
+
+#define HDMOE_MAX_EXPERTS 64
+#define HDMOE_MAX_TOPK 8
+
+int hdmoe_version(void);
+const char* hdmoe_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches counter) */
+int64_t hdmoe_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Router gate -- replaces Router.forward's tail, models/model_components.py:148-168, and emits the
+ *     load-balance / z-loss statistics of Utils/utils.py:158-172.
+ *
+ *     xmod   = pooled * (1 + gamma) + beta            (cond = [gamma | beta], NULL -> no modulation)
+ *     logits = xmod . w_hat^T  (+ zeta * noise)       (w_hat already weight-normalised, [E, C])
+ *     logits = -inf where mask == 0
+ *     gate_probs = softmax(logits);  (vals, idx) = top_k(logits)  [ties: lowest index];
+ *     topk_w = softmax(vals);  sparse_w = scatter(idx, topk_w)
+ *     stats[0:E]   = sum_t gate_probs[t, e]           (load_balance = E * sum_e (stats[e]/T)^2)
+ *     stats[E:2E]  = #tokens with sparse_w[t, e] > 0  (dispatch counts, as float)
+ *     stats[2E]    = sum_t min(logsumexp(clamp(logits, -50, 50))^2, 100)     (z_loss * T)
+ *     workspace: (grid * (2E+1) + 1) floats, the last one a zero-initialised ticket counter that the
+ *     kernel resets; use hdmoe_router_gate_workspace_bytes().
+ *     `logits_in` != NULL skips the linear part and gates the given (already masked) logits: the
+ *     teacher-forced entry used for bit-exact index parity.
+ * ---------------------------------------------------------------------------------------------- */
+size_t hdmoe_router_gate_workspace_bytes(int T, int E);
+int hdmoe_router_gate_fwd(const float* pooled, const float* cond, const float* w_hat, const float* noise,
+                          float zeta, const float* mask, const float* logits_in, int T, int C, int E, int top_k,
+                          float* logits, float* gate_probs, float* sparse_w, int32_t* topk_idx, float* topk_w,
+                          float* stats, void* workspace, hdmoe_stream_t stream);
+/* Backward of the above.  Any of the g_* may be NULL.  d_w_hat [E,C] is overwritten (not accumulated).
+ * g_stats has the layout of `stats`; only [0:E] and [2E] carry gradient. */
+int hdmoe_router_gate_bwd(const float* pooled, const float* cond, const float* w_hat, const float* logits,
+                          const int32_t* topk_idx, const float* g_sparse, const float* g_probs,
+                          const float* g_logits, const float* g_stats, int T, int C, int E, int top_k,
+                          float* d_pooled, float* d_cond, float* d_w_hat, float* d_logits_out,
+                          hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Dispatch plan + permute -- replaces the boolean-mask gathers of router_to_unet_experts,
+ *     models/model_config2.py:25-33 (== models/model_config1.py:25-33).
+ *
+ *     Row order is the reference's: expert-major, ascending token index inside an expert; an entry is
+ *     dispatched iff sparse_w[t, e] > 0 (NaN is not).  Integer outputs are bit-exact.
+ *       counts[E], offsets[E+1]                (offsets[E] = number of rows R)
+ *       row_src[cap], row_expert[cap], row_w[cap]   (valid for r < R; the tail is set to -1 / -1 / 0)
+ *       tok_rows[T, K]  row index of the j-th dispatched expert of token t (ascending e), -1 if none
+ *     cap >= R is required (cap = T * top_k always suffices); K >= max dispatched experts per token.
+ *     status[0] (device int) is set non-zero on overflow of cap or K.
+ * ---------------------------------------------------------------------------------------------- */
+size_t hdmoe_dispatch_plan_workspace_bytes(int T, int E);
+int hdmoe_dispatch_plan(const float* sparse_w, int T, int E, int cap, int K, int32_t* counts, int32_t* offsets,
+                        int32_t* row_src, int32_t* row_expert, float* row_w, int32_t* tok_rows,
+                        int32_t* status, void* workspace, hdmoe_stream_t stream);
+
+/* Gather rows: for up to 4 tensors at once, dst_i[r, :] = src_i[row_src[r], :] for r < *n_rows_dev
+ * (rows r in [*n_rows_dev, cap) are zero-filled).  Rows are raw bytes (row_bytes[i] % 16 == 0 and
+ * 16-byte-aligned bases take the 128-bit / bulk-copy paths; otherwise % 4 == 0 is required).
+ * srcs/dsts/row_bytes are HOST arrays of length n_tensors.  models/model_config2.py:31-33. */
+int hdmoe_permute_rows(const void* const* srcs, void* const* dsts, const int64_t* row_bytes, int n_tensors,
+                       const int32_t* row_src, const int32_t* n_rows_dev, int cap, hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Combine -- replaces `output = zeros_like(x); output[mask] += out_e * w[mask, e]`,
+ *     models/model_config2.py:23,35-37.  out[t,:] = (base ? base[t,:] : 0) + sum_j w_j * rows[r_j,:]
+ *     with r_j = tok_rows[t, j] >= 0 taken in ascending j (= ascending expert: the reference's
+ *     summation order; fp32 multiply then add, no FMA contraction, so fp32 results are bit-exact).
+ *     row_w == NULL means weight 1 (the backward of the permute).  `base` is the optional residual of
+ *     north_star item (4); the reference passes none.
+ * ---------------------------------------------------------------------------------------------- */
+int hdmoe_combine_rows(const void* rows, int rows_dtype, const int32_t* tok_rows, const float* row_w,
+                       const void* base, void* out, int out_dtype, int T, int K, int64_t D,
+                       hdmoe_stream_t stream);
+/* Backward of combine w.r.t. the expert rows and the gate weights:
+ *   d_rows[r,:] = row_w[r] * dY[row_src[r],:]            (r < R; tail rows zero-filled)
+ *   d_sparse_w[row_src[r], row_expert[r]] = <rows[r,:], dY[row_src[r],:]>   (d_sparse_w pre-zeroed by callee) */
+int hdmoe_combine_rows_bwd(const void* rows, int rows_dtype, const void* dY, int dy_dtype, const int32_t* row_src,
+                           const int32_t* row_expert, const float* row_w, const int32_t* n_rows_dev, int cap,
+                           int T, int E, int64_t D, void* d_rows, float* d_sparse_w, hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) EDM preconditioning and Heun step -- replaces models/model_config2.py:431-449 and
+ *     Utils/EDM_sampler.py:98-107 (+ the CFG lerp of :70).
+ *     sigma: device pointer to 1 value (sampler, 0-dim sigma) or B values (training).
+ *     Quirk Q1 is preserved: the skip connection uses the already scaled x_in = c_in * x.
+ * ---------------------------------------------------------------------------------------------- */
+/* x_in = x * c_in(sigma)  (x fp32 [B, n_per_sample]) */
+int hdmoe_edm_precond_in(const float* x, const float* sigma, int n_sigma, float sigma_data, void* x_in,
+                         int x_in_dtype, int64_t B, int64_t n_per_sample, hdmoe_stream_t stream);
+/* D = c_skip * x_in + c_out * F   (fp32 out) */
+int hdmoe_edm_precond_out(const void* x_in, int x_in_dtype, const void* F, int f_dtype, const float* sigma,
+                          int n_sigma, float sigma_data, float* D, int64_t B, int64_t n_per_sample,
+                          hdmoe_stream_t stream);
+/* backward of precond_out:  d_F = c_out * dD ;  d_x_in = c_skip * dD   (either output may be NULL) */
+int hdmoe_edm_precond_out_bwd(const float* dD, const float* sigma, int n_sigma, float sigma_data, void* dF,
+                              int df_dtype, void* d_xin, int dxin_dtype, int64_t B, int64_t n_per_sample,
+                              hdmoe_stream_t stream);
+/* backward of precond_in:   d_x = c_in * d_x_in   (fp32 out) */
+int hdmoe_edm_precond_in_bwd(const void* d_xin, int dxin_dtype, const float* sigma, int n_sigma, float sigma_data,
+                             float* dx, int64_t B, int64_t n_per_sample, hdmoe_stream_t stream);
+/* Heun step, stage A (Utils/EDM_sampler.py:98-99 + model_config2.py:440):
+ *   x_hat = x_cur + noise_scale * eps   (eps may be NULL when noise_scale == 0)
+ *   x_in  = x_hat * c_in(t_hat)                                                                   */
+int hdmoe_edm_heun_pre(const float* x_cur, const float* eps, float noise_scale, float t_hat, float sigma_data,
+                       float* x_hat, void* x_in, int x_in_dtype, int64_t n, hdmoe_stream_t stream);
+/* stage B (Euler, :100-102):  D = c_skip*x_in + c_out*F  [guided: D = Dg + guidance*(D - Dg)]
+ *   d_cur = (x_hat - D)/t_hat ; x_next = x_hat + (t_next - t_hat)*d_cur ; x_in_next = x_next*c_in(t_next)
+ * F_guide == NULL means guidance == 1.  t_next == 0 (last step) skips x_in_next.
+ * x_in == NULL: F (and F_guide) already are denoised estimates D of a foreign model.                */
+int hdmoe_edm_heun_euler(const float* x_hat, const void* x_in, int x_in_dtype, const void* F, const void* F_guide,
+                         int f_dtype, float guidance, float t_hat, float t_next, float sigma_data, float* d_cur,
+                         float* x_next, void* x_in_next, int64_t n, hdmoe_stream_t stream);
+/* stage C (2nd-order correction, :104-107):  D' from (x_in_next, F', t_next);
+ *   d' = (x_next - D')/t_next ; x_out = x_hat + (t_next - t_hat)*(0.5*d_cur + 0.5*d')             */
+int hdmoe_edm_heun_correct(const float* x_hat, const float* x_next, const void* x_in_next, int x_in_dtype,
+                           const void* F, const void* F_guide, int f_dtype, float guidance, float t_hat,
+                           float t_next, float sigma_data, const float* d_cur, float* x_out, int64_t n,
+                           hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5) W-PREP -- multi-tensor magnitude-preserving weight preparation; replaces the per-call weight
+ *     math of MP_Conv.forward, models/model_internals.py:253-260 (+ normalize, :26-30), for MANY
+ *     layers in one launch.  For row o of tensor i (fan_in = elements per row):
+ *        force != 0 (training):  w[o,:] <- w[o,:] / (eps + ||w[o,:]|| / sqrt(fan_in))     (in place, Q6)
+ *        w_hat[o,:] = w[o,:] / (eps + ||w[o,:]|| / sqrt(fan_in)) * gain / sqrt(fan_in)
+ *     Output layout HDMOE_WLAYOUT_SAME keeps [rows][fan_in]; HDMOE_WLAYOUT_TAPS writes the implicit-GEMM
+ *     layout [tap][rows][cin_pad] (K-major, zero padded) consumed by hdmoe_grouped_conv_fwd.
+ * ---------------------------------------------------------------------------------------------- */
+#define HDMOE_WLAYOUT_SAME 0
+#define HDMOE_WLAYOUT_TAPS 1
+typedef struct {
+    float* w;               /* [rows][fan_in] fp32 master weights (mutated when force != 0)         */
+    void* w_hat;            /* output                                                                */
+    const float* gain_ptr;  /* optional device scalar gain (e.g. Unet_expert.out_gain); NULL -> gain */
+    float gain;
+    int32_t rows, fan_in;   /* fan_in = cin * taps                                                   */
+    int32_t cin, taps, cin_pad;
+    int32_t out_dtype, layout;
+    int32_t block_start;    /* filled by the callee's host wrapper: first CTA of this tensor        */
+} hdmoe_wprep_desc;
+/* descs: HOST array of n descriptors (copied to `descs_dev`, a device buffer of n*sizeof(desc) bytes). */
+int hdmoe_wprep_fwd(hdmoe_wprep_desc* descs_host, void* descs_dev, int n, int force, hdmoe_stream_t stream);
+/* d_w[o,:] from d_w_hat[o,:] (layout SAME, fp32), through ONE normalisation (the gradient path of
+ * models/model_internals.py:258-259).  d_gain (device scalar, accumulated) may be NULL. */
+int hdmoe_wprep_bwd(const float* w, const float* d_w_hat, const float* gain_ptr, float gain, int rows, int fan_in,
+                    float* d_w, float* d_gain, hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (6) Grouped implicit-GEMM convolution / GEMM on tcgen05 + TMEM + TMA -- replaces the F.conv2d /
+ *     F.linear calls of MP_Conv inside the experts (models/model_internals.py:261-271), for ALL
+ *     experts of one layer in a single persistent launch.  Declared in hdmoe_gemm.h.
+ * ---------------------------------------------------------------------------------------------- */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDMOE_B200_H_ */

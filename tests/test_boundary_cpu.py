@@ -1,0 +1,135 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library exports every symbol the header declares,
+the Python modules keep the reference's interface (constructor / forward signatures, state_dict keys, init
+RNG order), the host-side producers match the reference fixtures, and nothing falls back to the CPU."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+import hdmoe_b200
+from conftest import ROOT, TINY, golden_weights, load_golden
+from hdmoe_b200 import _lib, ops
+from hdmoe_b200 import model_components as mc
+from hdmoe_b200 import model_config1 as c1
+from hdmoe_b200 import model_config2 as c2
+from hdmoe_b200.EDM_sampler import EDM_Sampler
+from hdmoe_b200.utils import EDM_LOSS, MaskGenerator, ZetaScheduler
+
+
+def _header_symbols():
+    names = set()
+    for h in os.listdir(os.path.join(ROOT, "include")):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(hdmoe_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "libhdmoe_b200.so not built (run `make`)"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ but not exported"
+        assert s in _lib.PROTOTYPES, f"{s} has no ctypes prototype"
+    assert set(_lib.PROTOTYPES) == set(syms)
+    assert _lib.lib().hdmoe_version() >= 100
+
+
+def test_no_cpu_fallback():
+    w = torch.rand(8, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.dispatch_plan(w)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.router_gate(torch.rand(8, 16), None, torch.rand(4, 16), 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.edm_precond_in(torch.rand(2, 4, 4, 4), torch.ones(2), 0.5)
+
+
+def test_argument_errors_are_reported():
+    lib = _lib.lib()
+    rc = lib.hdmoe_router_gate_fwd(None, None, None, None, 0.0, None, None, 4, 16, 99, 1, None, None, None, None,
+                                   None, None, None, None)
+    assert rc == -1 and b"E <=" in lib.hdmoe_last_error()
+    with pytest.raises(RuntimeError, match="code -1"):
+        _lib.check(rc, "router_gate_fwd")
+
+
+# reference signatures (models/model_components.py:79-85,18-22,281-293,589-604; model_config2.py:331-355;
+# Utils/EDM_sampler.py:7-20,34-35,72-79)
+REF_SIGS = {
+    (mc.Router, "__init__"): ["in_channels", "time_dim", "top_k", "num_experts", "dropout"],
+    (mc.Router, "forward"): ["x", "time_emb", "mask", "zeta"],
+    (mc.Scaling_router, "__init__"): ["emb_dim", "num_experts", "dropout"],
+    (mc.Scaling_router, "forward"): ["x", "zeta"],
+    (mc.Unet_expert, "__init__"): ["img_resolution", "img_channels", "time_emb_dim", "text_emb_dim", "channel_mult",
+                                   "model_channels", "channel_mult_emb", "num_blocks", "kernel_size", "label_balance",
+                                   "concat_balance"],
+    (mc.Unet_expert, "forward"): ["x", "time_emb", "text_emb"],
+    (mc.Vit_expert, "__init__"): ["num_heads", "num_groups", "in_channels", "seq_ln", "emb_dim", "num_blocks",
+                                  "patch_size", "time_dim", "text_dim", "res_balance", "attn_balance", "emb_balance",
+                                  "gain_s", "gain_t"],
+    (mc.Vit_expert, "forward"): ["x", "time_emb", "text_emb"],
+    (c2.preconditioned_HDMOEM, "forward"): ["x", "sigma", "text_emb", "Unet_router_mask", "Vit_router_mask", "zeta",
+                                            "transition_point", "softness", "return_log_var"],
+    (c1.preconditioned_HDMOEM, "forward"): ["x", "sigma", "text_emb", "Unet_router_mask", "Vit_router_mask", "zeta",
+                                            "return_log_var"],
+    (c2.HDMOEM, "forward"): ["x", "time_vec", "text_emb", "Unet_router_mask", "Vit_router_mask", "zeta",
+                             "transition_point", "softness"],
+    (EDM_Sampler, "__init__"): ["model", "Guide_net", "num_solve_steps", "sigma_min", "sigma_max", "rho", "S_churn",
+                                "S_min", "S_max", "S_noise", "guidance", "dtype"],
+    (EDM_Sampler, "denoise"): ["x", "sigma", "text_emb", "transition_mean", "softness", "uncond_text_emb"],
+    (EDM_Sampler, "sample"): ["noise", "text_emb", "transition_mean", "softness", "uncond_text_emb"],
+}
+
+
+@pytest.mark.parametrize("key", list(REF_SIGS), ids=lambda k: f"{k[0].__name__}.{k[1]}")
+def test_reference_signatures(key):
+    cls, meth = key
+    params = [p for p in inspect.signature(getattr(cls, meth)).parameters if p != "self"]
+    ref = REF_SIGS[key]
+    assert params[:len(ref)] == ref     # extra trailing keyword-only conveniences (noise=...) are allowed
+    assert c2.router_to_unet_experts.__name__ == "router_to_unet_experts"
+    assert list(inspect.signature(c2.router_to_unet_experts).parameters)[:5] == ["x", "experts", "out_router",
+                                                                                 "time_emb", "text_emb"]
+
+
+@pytest.mark.parametrize("variant,wfile", [(2, "weights_cfg2_seed0"), (1, "weights_cfg1_seed0")])
+def test_state_dict_layout_and_init_order_match_reference(variant, wfile):
+    """Same seed -> same parameters as the reference constructor (so checkpoints and seeds interchange)."""
+    ref = load_golden(wfile)
+    torch.manual_seed(0)
+    model = (c2 if variant == 2 else c1).preconditioned_HDMOEM(**TINY)
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    n_checked = 0
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(ref[k].shape), k
+        if float(v.abs().max()) != 0:          # zero-initialised entries were re-drawn in the fixture
+            assert torch.equal(v, ref[k]), k
+            n_checked += 1
+    assert n_checked > 100
+    model.load_state_dict(ref)
+    assert model.num_experts == 4 and hasattr(model.net, "Unet_router") and hasattr(model.net, "VIT_experts")
+
+
+def test_host_producers_match_reference():
+    g = load_golden("producers")
+    sigma = g["mask.sigma"]
+    for tag, attrs, rng in (("unet", [3, 3, 5, 5], (0.0, 0.6)), ("vit", [4, 8, 8, 16], (0.4, 1.0))):
+        mg = MaskGenerator(expert_attributes=attrs, p_mean=-1.2, p_std=1.6, bandwidth=0.3, max_bandwidth=0.8,
+                           min_active=1, total_steps=5000, step_size=0.1, noise_range=rng, strat_band="step")
+        assert torch.equal(mg.expert_centers, g[f"mask.{tag}.centers"])
+        for step in (0, 700, 2600, 6000):
+            assert torch.equal(mg(sigma, step), g[f"mask.{tag}.{step}"])
+    for strat in ("cos", "exp"):
+        zs = ZetaScheduler(total_steps=900, max_zeta=2, min_zeta=0.01, strategy=strat, alpha=4.0, warmup_ratio=0.05)
+        for i, s in enumerate(g["zeta.steps"].tolist()):
+            assert abs(zs.get_zeta(s) - float(g[f"zeta.{strat}"][i])) < 1e-12
+    smp = EDM_Sampler(None, None, num_solve_steps=18)
+    assert torch.equal(smp.t_steps()[:-1], g["sampler.t_steps18"])
+    assert abs(float(EDM_LOSS.load_balance(torch.full((16, 4), 0.25), 4)) - 1.0) < 1e-6
