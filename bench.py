@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native heterogeneous-MoE hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|sample]
+
+Workload at N=1 (BASELINE.json configs[1]): model_config1 training step, bf16 expert path, batch 256 per GPU,
+4x32x32 VAE-shaped latents, CLIP-shaped random text embeddings (256,77,768), random-init weights (zero-init
+parameters re-drawn from N(0,0.3^2)).  One step = forward(return_log_var=True) + EDM_LOSS + backward +
+clip_grad_norm_(1.0) + AdamW over ALL parameters.  N>1: one process per GPU
+(torchrun), data-parallel replicas of the step with an NCCL gradient all-reduce; weak scaling.
+
+Prints ONE JSON line (see the repo brief for the contract): value = whole-job img/s with inputs resident in
+HBM; e2e = the same metric through the public module API with pinned HOST inputs, H2D copies and the D2H loss
+read inside the timed region; roofline = the dominant hand-written kernel timed live with CUDA events;
+cpu_baseline = the CPU oracle (a port of the reference) timed on this box's host cores on a bounded sample.
+`--impl reference` times only that CPU arm, on all host threads, and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FULL = dict(IN_in_channels=4, IN_img_resolution=32, internal_channels=32, time_emb_dim=64, text_emb_dim=768,
+            num_experts=4, top_k=1, Fourier_bandwidth=1.0, VIT_num_blocks=4, VIT_patch_sizes=[4, 8, 8, 16],
+            VIT_num_groups=4, VIT_num_heads=8, VIT_emb_size=32, Unet_num_blocks=2, Unet_channel_mult=[1, 2],
+            Unet_kernel_sizes=[(3, 3), (3, 3), (5, 5), (5, 5)], Unet_model_channels=32, Unet_channel_mult_emb=2,
+            Unet_label_balance=0.5, Unet_concat_balance=0.5, sigma_data=0.5, log_var_channels=32)
+LOSS = dict(num_experts=4, sigma_data=0.5, Unet_bal=0.05, vit_bal=0.1, z_bal=0.005, prior_bal=0.0)
+MASK = dict(p_mean=-1.2, p_std=1.6, bandwidth=0.3, max_bandwidth=0.8, min_active=1, total_steps=5000, step_size=0.1,
+            strat_band="step")
+P_MEAN, P_STD = -1.2, 1.6
+SEED = 1234
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sus=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+def synth_batch(B, res, rank, device, pinned=False):
+    """Synthetic step inputs on the HOST (seed 1234 + rank): latents, sigma, noised latents, text, masks."""
+    from hdmoe_b200.utils import MaskGenerator, sample_sigma_hybrid
+    gen = torch.Generator().manual_seed(SEED + rank)
+    x0 = torch.randn(B, 4, res, res, generator=gen) * 0.5
+    sigma = sample_sigma_hybrid(B, 0.002, 80.0, p_mean=P_MEAN, p_std=P_STD, extreme_prob=0.5, device="cpu",
+                                generator=gen)
+    x = x0 + sigma * torch.randn(x0.shape, generator=gen)
+    text = torch.randn(B, 77, 768, generator=gen)
+    um = MaskGenerator([3, 3, 5, 5], noise_range=(0.0, 0.6), **MASK)(sigma, 0)
+    vm = MaskGenerator([4, 8, 8, 16], noise_range=(0.4, 1.0), **MASK)(sigma, 0)
+    batch = dict(x0=x0, sigma=sigma, x=x, text=text, um=um, vm=vm)
+    if pinned:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    return batch
+
+
+def build_model(variant, device, seed=0):
+    import hdmoe_b200
+    mod = hdmoe_b200.model_config1 if variant == 1 else hdmoe_b200.model_config2
+    torch.manual_seed(seed)
+    model = mod.preconditioned_HDMOEM(**FULL)
+    gen = torch.Generator().manual_seed(seed + 100)
+    with torch.no_grad():
+        for p in model.parameters():
+            if float(p.abs().max()) == 0:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
+    return model.to(device)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(v, world, device):
+    if world == 1:
+        return v
+    import torch.distributed as dist
+    t = torch.tensor([v], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+class L2Flusher:
+    def __init__(self, device):
+        self.buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def __call__(self):
+        self.buf.add_(1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import hdmoe_b200
+    from hdmoe_b200 import _lib
+    from hdmoe_b200.utils import EDM_LOSS
+    rank, world, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    _lib.lib()     # fail loudly if the CUDA library is missing
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    hdmoe_b200.set_expert_dtype(torch.bfloat16)
+    B = args.batch
+    model = build_model(1, device)
+    model.train()
+    crit = EDM_LOSS(**LOSS)
+    params = [p for p in model.parameters()]
+    opt = torch.optim.AdamW(params, lr=5e-4, fused=True)
+    flat_sizes = [p.numel() for p in params]
+    host = synth_batch(B, 32, rank, device, pinned=True)
+    dev_batch = {k: v.to(device) for k, v in host.items()}
+    zeta = 2.0
+    flush = L2Flusher(device)
+
+    def step(b):
+        out = model(x=b["x"], sigma=b["sigma"], text_emb=b["text"], Unet_router_mask=b["um"],
+                    Vit_router_mask=b["vm"], zeta=zeta, return_log_var=True)
+        loss = crit(b["sigma"], b["x0"], b["sigma"], out)
+        opt.zero_grad(set_to_none=True)
+        loss["loss"].backward()
+        if world > 1:
+            import torch.distributed as dist
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            flat.div_(world)
+            for p, g in zip(params, flat.split(flat_sizes)):
+                p.grad = g.view_as(p)
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss["loss"]
+
+    for _ in range(args.warmup):
+        step(dev_batch)
+    barrier(world)
+
+    # ---- device-resident timing: K steps, CUDA events per step, L2 flushed between steps (not timed)
+    clocks = ClockSampler(local)
+    l0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier(world)
+    for s, e in ev:
+        flush()
+        s.record()
+        step(dev_batch)
+        e.record()
+    barrier(world)
+    launches = _lib.launch_count() - l0
+    ms_total = sum(s.elapsed_time(e) for s, e in ev)
+    ms_total = max_over_ranks(ms_total, world, device)
+    clk = clocks.stop()
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1e3)
+
+    # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, all inside the timed region
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier(world)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    loss_host = 0.0
+    for _ in range(e2e_steps):
+        b = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        loss_host = float(step(b).item())        # D2H read of the step result
+    e.record()
+    barrier(world)
+    e2e_ms = max_over_ranks(s.elapsed_time(e), world, device) / e2e_steps
+    e2e_value = B * world / (e2e_ms / 1e3)
+
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        roof = roofline_dispatch(device, peaks, flush)
+        cpu = cpu_baseline_train(sample_batch=8, iters=3)
+        line = {"metric": "denoiser train img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": "model_config1 train step (fwd+EDM_LOSS+bwd+clip+AdamW), batch 256/GPU, "
+                                       "4x32x32 latent, text (B,77,768), bf16 expert path, fp32 trunk (TF32 matmul)",
+                           "global_batch": B * world, "parallelism": f"dp{world}",
+                           "l2": "L2 flushed (256 MiB write) between timed steps, outside the timed events"},
+                "clocks": clk,
+                "e2e": {"value": round(e2e_value, 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3), "last_loss": loss_host},
+                "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu, "peaks": peaks["src"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return line
+
+
+def roofline_dispatch(device, peaks, flush, T=256, E=4, D=32 * 32 * 32, iters=20):
+    """Dominant hand-written kernel of the current step: the MoE row gather + gate-weighted combine at the
+    training shape (256 rows of 32x32x32 bf16 = 64 KiB).  achieved = algorithmic bytes / CUDA-event time."""
+    from hdmoe_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    lg = torch.randn(T, E, generator=gen)
+    sp = torch.zeros(T, E).scatter_(1, lg.argmax(1, keepdim=True), 1.0).to(device)
+    x = torch.randn(T, D, generator=gen).to(device=device, dtype=torch.bfloat16)
+    plan = ops.dispatch_plan(sp, top_k=1)
+    rows = ops.permute(plan, x)[0]
+    out = ops.combine(rows, sp, plan)
+    tp = tc = 0.0
+    for i in range(iters + 3):
+        flush()
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        rows = ops.permute(plan, x)[0]
+        b.record()
+        out = ops.combine(rows, sp, plan)
+        c.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            tp += a.elapsed_time(b)
+            tc += b.elapsed_time(c)
+    R, s = T, 2
+    bytes_p = 2 * R * D * s + R * 4                     # rows read + written + index
+    bytes_c = R * D * s + R * 8 + T * D * s
+    ach = (bytes_p + bytes_c) / ((tp + tc) / iters * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "permute_bulk_kernel + combine_kernel (T=256, 64 KiB bf16 rows)",
+            "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4),
+            "traffic": None, "permute_us": round(tp / iters * 1e3, 2), "combine_us": round(tc / iters * 1e3, 2),
+            "algorithmic_bytes": bytes_p + bytes_c}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (a port of the reference's algorithm) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_baseline_train(sample_batch=8, iters=3, warmup=1):
+    from oracle import hdmoe_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = build_model(1, "cpu")
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(("freqs", "phases")))
+          for k, v in model.state_dict().items()}
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=5e-4)
+    b = synth_batch(sample_batch, 32, 0, "cpu")
+    gen = torch.Generator().manual_seed(7)
+
+    def step():
+        noise = {"scaling": torch.randn(sample_batch, 2, generator=gen),
+                 "vit": torch.randn(sample_batch, 4, generator=gen), "unet": torch.randn(sample_batch, 4, generator=gen)}
+        with O.training_mode():
+            out = O.preconditioned(sd, FULL, b["x"], b["sigma"], b["text"], b["um"], b["vm"], zeta=2.0,
+                                   return_log_var=True, noise=noise, variant=1)
+        loss = O.edm_loss(b["x0"], out, 4, LOSS["Unet_bal"], LOSS["vit_bal"], LOSS["z_bal"])["loss"]
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    dt = (time.perf_counter() - t0) / iters
+    return {"value": round(sample_batch / dt, 3), "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"oracle (CPU port of the reference) model_config1 train step, batch {sample_batch}, fp32, "
+                      f"{iters} steps after {warmup} warm-up, dropout off", "s_per_step": round(dt, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    iters = max(1, min(args.steps, 5))
+    cpu = cpu_baseline_train(sample_batch=8, iters=iters, warmup=max(1, min(args.warmup, 2)))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    line = {"impl": "reference", "metric": "denoiser train img/s", "value": cpu["value"], "unit": "img/s",
+            "n_gpus": world, "steps": iters, "warmup": max(1, min(args.warmup, 2)),
+            "ms_per_step": round(cpu["s_per_step"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "model_config1 train step (fwd+EDM_LOSS+bwd+clip+AdamW), bounded sample batch 8, "
+                                   "4x32x32 latent, text (8,77,768), CPU fp32", "global_batch": 8,
+                       "parallelism": "cpu"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py (impl ours) needs a CUDA device: hdmoe_b200 has no CPU fallback")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
