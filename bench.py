@@ -207,11 +207,17 @@ def run_ours(args):
     l0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier(world)
-    for s, e in ev:
+    for i, (s, e) in enumerate(ev):
         flush()
+        if args.profile_step and i == 0:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()      # ncu --profile-from-start off captures exactly one timed step
         s.record()
         step(dev_batch)
         e.record()
+        if args.profile_step and i == 0:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
     barrier(world)
     launches = _lib.launch_count() - l0
     ms_total = sum(s.elapsed_time(e) for s, e in ev)
@@ -358,6 +364,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile-step", action="store_true", help="cudaProfilerStart/Stop around the first timed step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -19,6 +19,6 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace hdmoe
 
-extern "C" int hdmoe_version(void) { return 100; }
+extern "C" int hdmoe_version(void) { return 101; }
 extern "C" const char* hdmoe_last_error(void) { return hdmoe::g_err; }
 extern "C" int64_t hdmoe_launch_count(void) { return hdmoe::g_launches.load(std::memory_order_relaxed); }

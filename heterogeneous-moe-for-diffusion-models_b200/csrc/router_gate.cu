@@ -410,7 +410,7 @@ static int gate_grid(int T) {
 using namespace hdmoe;
 
 extern "C" size_t hdmoe_router_gate_workspace_bytes(int T, int E) {
-    return ((size_t)gate_grid(T) * (2 * E + 1) + 1) * sizeof(float);
+    return ((size_t)gate_grid(T) * (2 * E + 1) + 4) * sizeof(float);
 }
 
 #define GATE_DISPATCH(EPV, KERNEL, SMEM, ...)                                                              \
@@ -435,8 +435,9 @@ extern "C" int hdmoe_router_gate_fwd(const float* pooled, const float* cond, con
     cudaStream_t st = (cudaStream_t)stream;
     const int EP = pad_experts(E);
     const int grid = gate_grid(T);
-    float* partial = (float*)workspace;
-    unsigned* ticket = (unsigned*)(partial + (size_t)grid * (2 * E + 1));
+    // the ticket sits at a FIXED offset (word 0) so that calls with different grids share one zeroed counter
+    unsigned* ticket = (unsigned*)workspace;
+    float* partial = (float*)workspace + 4;
     if (T == 0) {
         HDMOE_CHECK_CUDA(cudaMemsetAsync(stats, 0, (2 * E + 1) * sizeof(float), st));
         return HDMOE_OK;

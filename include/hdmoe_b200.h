@@ -55,8 +55,8 @@ int64_t hdmoe_launch_count(void);
  *     stats[0:E]   = sum_t gate_probs[t, e]           (load_balance = E * sum_e (stats[e]/T)^2)
  *     stats[E:2E]  = #tokens with sparse_w[t, e] > 0  (dispatch counts, as float)
  *     stats[2E]    = sum_t min(logsumexp(clamp(logits, -50, 50))^2, 100)     (z_loss * T)
- *     workspace: (grid * (2E+1) + 1) floats, the last one a zero-initialised ticket counter that the
- *     kernel resets; use hdmoe_router_gate_workspace_bytes().
+ *     workspace: word 0 is a zero-initialised ticket counter (the kernel resets it), per-CTA partials follow;
+ *     size from hdmoe_router_gate_workspace_bytes().
  *     `logits_in` != NULL skips the linear part and gates the given (already masked) logits: the
  *     teacher-forced entry used for bit-exact index parity.
  * ---------------------------------------------------------------------------------------------- */
