@@ -25,6 +25,14 @@ def get_expert_dtype() -> torch.dtype:
     return _EXPERT_DTYPE[0]
 
 
+# grouped tcgen05 execution of the U-Net experts (bf16 expert path only); the switch exists for A/B parity tests
+_GROUPED = [True]
+
+
+def set_grouped_experts(enabled: bool) -> None:
+    _GROUPED[0] = bool(enabled)
+
+
 def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: torch.Tensor,
                            time_emb: torch.Tensor, text_emb: Optional[torch.Tensor],
                            top_k: Optional[int] = None) -> torch.Tensor:
@@ -42,6 +50,15 @@ def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: 
     rows = ops.permute(plan, *srcs)
     xr, tr = rows[0], rows[1]
     txr = rows[2] if text_emb is not None else None
+    if (dt == torch.bfloat16 and _GROUPED[0] and len(experts) > 0
+            and all(isinstance(ex, mc.Unet_expert) for ex in experts) and _groupable(experts, xr)):
+        from .grouped import GroupedUnetExperts
+        runner = experts.__dict__.get("_hdmoe_grouped")
+        if runner is None:
+            runner = GroupedUnetExperts(experts)
+            experts.__dict__["_hdmoe_grouped"] = runner
+        out_rows = runner(plan, xr, tr, txr, training=experts[0].training)
+        return ops.combine(out_rows.contiguous(), out_router, plan, base=None, out_dtype=x.dtype)
     off = plan.host_offsets()
     outs = []
     for e, expert in enumerate(experts):
@@ -54,6 +71,20 @@ def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: 
         outs.append(xr.new_zeros((plan.cap - R,) + tuple(xr.shape[1:])))
     out_rows = torch.cat(outs, dim=0) if len(outs) != 1 else outs[0]
     return ops.combine(out_rows, out_router, plan, base=None, out_dtype=x.dtype)
+
+
+def _groupable(experts, xr) -> bool:
+    """Shape constraints of the tcgen05 grouped convolution (include/hdmoe_gemm.h)."""
+    H, W = xr.shape[-2], xr.shape[-1]
+    e0 = experts[0]
+    levels = len(e0.block_channels)
+    for lv in range(levels):
+        h, w = H >> lv, W >> lv
+        if w < 1 or 128 % w != 0 or (h * w) % 128 != 0 or h % (128 // w) != 0:
+            return False
+    chans = set(e0.block_channels) | {xr.shape[1]}
+    return all(c in (32, 64, 128) for c in chans) and all(k[0] == k[1] and k[0] % 2 == 1 for k in
+                                                          (ex.kernel_size for ex in experts))
 
 
 class HDMOEM(nn.Module):

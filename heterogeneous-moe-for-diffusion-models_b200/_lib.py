@@ -10,15 +10,22 @@ LIB_PATH = os.path.join(_HERE, "lib", "libhdmoe_b200.so")
 
 F32, BF16 = 0, 1
 MAX_EXPERTS, MAX_TOPK = 64, 8
-WLAYOUT_SAME, WLAYOUT_TAPS = 0, 1
+WLAYOUT_SAME, WLAYOUT_TAPS, WLAYOUT_TAPS_T = 0, 1, 2
 
 _p, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 
 
 class WprepDesc(C.Structure):
-    _fields_ = [("w", _p), ("w_hat", _p), ("gain_ptr", _p), ("gain", _f), ("rows", C.c_int32), ("fan_in", C.c_int32),
-                ("cin", C.c_int32), ("taps", C.c_int32), ("cin_pad", C.c_int32), ("out_dtype", C.c_int32),
-                ("layout", C.c_int32), ("block_start", C.c_int32)]
+    _fields_ = [("w", _p), ("w_hat", _p), ("w_hat2", _p), ("gain_ptr", _p), ("active", _p), ("gain", _f),
+                ("rows", C.c_int32), ("fan_in", C.c_int32), ("cin", C.c_int32), ("taps", C.c_int32),
+                ("cin_pad", C.c_int32), ("cin_rows", C.c_int32), ("cout_pad", C.c_int32), ("out_dtype", C.c_int32),
+                ("layout", C.c_int32), ("layout2", C.c_int32), ("block_start", C.c_int32)]
+
+
+class WprepBwdDesc(C.Structure):
+    _fields_ = [("w", _p), ("d_w_hat", _p), ("gain_ptr", _p), ("d_w", _p), ("d_gain", _p), ("gain", _f),
+                ("rows", C.c_int32), ("fan_in", C.c_int32), ("cin", C.c_int32), ("taps", C.c_int32),
+                ("cin_pad", C.c_int32), ("layout", C.c_int32), ("block_start", C.c_int32)]
 
 
 # name -> (restype, argtypes); mirrors include/hdmoe_b200.h one to one
@@ -43,6 +50,7 @@ PROTOTYPES = {
     "hdmoe_edm_heun_correct": (_i, [_p, _p, _p, _i, _p, _p, _i, _f, _f, _f, _f, _p, _p, _i64, _p]),
     "hdmoe_wprep_fwd": (_i, [_p, _p, _i, _i, _p]),
     "hdmoe_gconv_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
+    "hdmoe_wprep_bwd_multi": (_i, [_p, _p, _i, _p]),
     "hdmoe_wprep_bwd": (_i, [_p, _p, _p, _f, _i, _i, _p, _p, _p]),
 }
 

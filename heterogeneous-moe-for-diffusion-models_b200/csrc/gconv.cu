@@ -134,7 +134,7 @@ struct ConvCfg {
     static constexpr int B_UNIT = N * KC * 2;
     static constexpr int STAGE = UPS * (A_UNIT + B_UNIT);
     static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
-    static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+    static constexpr int TMEM_COLS = 2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : 256);
     static constexpr int SMEM = STAGES * STAGE + 1024;        // + alignment slack
 };
 
@@ -271,7 +271,13 @@ gconv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t acc_phase = 0;
         for (int i = blockIdx.x; i < p.n_tiles; i += gridDim.x) {
             int r, pb, e;
-            if (!tile_at(i, r, pb, e)) continue;
+            if (!tile_at(i, r, pb, e)) {
+                // unused tail row: define the output (zeros) so that downstream elementwise ops stay finite
+                __nv_bfloat16* o = p.Y + (((size_t)r * p.H + (size_t)(pb * p.BH + hh)) * p.W + ww) * N;
+#pragma unroll
+                for (int q = 0; q < N / 8; ++q) *reinterpret_cast<int4*>(o + 8 * q) = make_int4(0, 0, 0, 0);
+                continue;
+            }
             mb_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const size_t pix_off = (((size_t)r * p.H + (size_t)(pb * p.BH + hh)) * p.W + ww) * N;
@@ -360,7 +366,7 @@ extern "C" int hdmoe_gconv_fwd(const void* X, const void* Wt, void* Y, int cap_r
                                int act, const void* residual, float res_a, float res_b, hdmoe_stream_t stream) {
     HDMOE_CHECK_ARG(X && Wt && Y && row_expert && n_rows_dev && ksize_host && wrow_host, "gconv_fwd: null pointer");
     HDMOE_CHECK_ARG(n_experts >= 1 && n_experts <= kMaxE, "gconv_fwd: 1 <= n_experts <= %d", kMaxE);
-    HDMOE_CHECK_ARG(Cout == 32 || Cout == 64 || Cout == 128, "gconv_fwd: Cout must be 32, 64 or 128 (got %d)", Cout);
+    HDMOE_CHECK_ARG(Cout == 32 || Cout == 64 || Cout == 96 || Cout == 128, "gconv_fwd: Cout must be 32, 64, 96 or 128 (got %d)", Cout);
     HDMOE_CHECK_ARG(Cin_pad >= 32 && Cin_pad % 32 == 0, "gconv_fwd: Cin_pad must be a multiple of 32 (got %d)", Cin_pad);
     HDMOE_CHECK_ARG(W >= 1 && W <= 128 && 128 % W == 0 && (H * W) % 128 == 0 && H % (128 / W) == 0,
                     "gconv_fwd: need W | 128 and 128 | H*W (got %dx%d)", H, W);
@@ -425,7 +431,7 @@ extern "C" int hdmoe_gconv_fwd(const void* X, const void* Wt, void* Y, int cap_r
     cudaStream_t st = (cudaStream_t)stream;
 #define GC(KCV, NV) \
     if (KC == KCV && Cout == NV) return launch_gconv<KCV, NV>(ta, tb, p, st);
-    GC(32, 32) GC(32, 64) GC(32, 128) GC(64, 32) GC(64, 64) GC(64, 128)
+    GC(32, 32) GC(32, 64) GC(32, 96) GC(32, 128) GC(64, 32) GC(64, 64) GC(64, 96) GC(64, 128)
 #undef GC
     HDMOE_CHECK_ARG(false, "gconv_fwd: unsupported (KC=%d, Cout=%d)", KC, Cout);
 }

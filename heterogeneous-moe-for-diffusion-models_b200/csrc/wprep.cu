@@ -23,6 +23,41 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return s;
 }
 
+template <typename T>
+__device__ __forceinline__ void put(void* base, size_t i, float v);
+template <>
+__device__ __forceinline__ void put<float>(void* base, size_t i, float v) { ((float*)base)[i] = v; }
+template <>
+__device__ __forceinline__ void put<__nv_bfloat16>(void* base, size_t i, float v) {
+    ((__nv_bfloat16*)base)[i] = __float2bfloat16_rn(v);
+}
+
+template <typename T>
+__device__ __forceinline__ void emit_row_t(const hdmoe_wprep_desc& d, int layout, void* out, const float* w, int row,
+                                           float scale) {
+    if (layout == HDMOE_WLAYOUT_SAME) {
+        for (int i = threadIdx.x; i < d.fan_in; i += kWprepThreads) put<T>(out, (size_t)row * d.fan_in + i, w[i] * scale);
+    } else if (layout == HDMOE_WLAYOUT_TAPS) {
+        // source row is [cin][taps]; destination is [tap][rows][cin_pad]
+        for (int i = threadIdx.x; i < d.taps * d.cin_pad; i += kWprepThreads) {
+            const int tap = i / d.cin_pad, c = i - tap * d.cin_pad;
+            const float v = c < d.cin ? w[(size_t)c * d.taps + tap] * scale : 0.f;
+            put<T>(out, ((size_t)tap * d.rows + row) * d.cin_pad + c, v);
+        }
+    } else {
+        // data-gradient operand: destination [taps-1-tap][cin_rows][cout_pad], this CTA owns column `row`
+        for (int i = threadIdx.x; i < d.taps * d.cin_rows; i += kWprepThreads) {
+            const int tap = i / d.cin_rows, c = i - tap * d.cin_rows;
+            put<T>(out, ((size_t)(d.taps - 1 - tap) * d.cin_rows + c) * d.cout_pad + row, w[(size_t)c * d.taps + tap] * scale);
+        }
+    }
+}
+__device__ __forceinline__ void emit_row(const hdmoe_wprep_desc& d, int layout, void* out, const float* w, int row,
+                                         float scale) {
+    if (d.out_dtype == HDMOE_F32) emit_row_t<float>(d, layout, out, w, row, scale);
+    else emit_row_t<__nv_bfloat16>(d, layout, out, w, row, scale);
+}
+
 __global__ void __launch_bounds__(kWprepThreads)
 wprep_fwd_kernel(const hdmoe_wprep_desc* __restrict__ descs, int n, int force) {
     __shared__ float red[kWprepThreads / 32];
@@ -41,7 +76,7 @@ wprep_fwd_kernel(const hdmoe_wprep_desc* __restrict__ descs, int n, int force) {
     for (int i = threadIdx.x; i < d.fan_in; i += kWprepThreads) { const float v = w[i]; ss += v * v; }
     float nrm = sqrtf(block_sum(ss, red));
     float inv = 1.f / (kEps + alpha * nrm);
-    if (force) {
+    if (force && (!d.active || *d.active != 0)) {
         // weights <- normalize(weights); the forward then normalises the REWRITTEN values once more
         float ss2 = 0.f;
         for (int i = threadIdx.x; i < d.fan_in; i += kWprepThreads) {
@@ -54,24 +89,8 @@ wprep_fwd_kernel(const hdmoe_wprep_desc* __restrict__ descs, int n, int force) {
     }
     const float gain = d.gain_ptr ? *d.gain_ptr : d.gain;
     const float scale = inv * gain * alpha;
-    if (d.layout == HDMOE_WLAYOUT_SAME) {
-        if (d.out_dtype == HDMOE_F32) {
-            float* o = (float*)d.w_hat + (size_t)row * d.fan_in;
-            for (int i = threadIdx.x; i < d.fan_in; i += kWprepThreads) o[i] = w[i] * scale;
-        } else {
-            __nv_bfloat16* o = (__nv_bfloat16*)d.w_hat + (size_t)row * d.fan_in;
-            for (int i = threadIdx.x; i < d.fan_in; i += kWprepThreads) o[i] = __float2bfloat16_rn(w[i] * scale);
-        }
-    } else {
-        // source row is [cin][taps]; destination is [tap][rows][cin_pad]
-        for (int i = threadIdx.x; i < d.taps * d.cin_pad; i += kWprepThreads) {
-            const int tap = i / d.cin_pad, c = i - tap * d.cin_pad;
-            const float v = c < d.cin ? w[(size_t)c * d.taps + tap] * scale : 0.f;
-            const size_t o = ((size_t)tap * d.rows + row) * d.cin_pad + c;
-            if (d.out_dtype == HDMOE_F32) ((float*)d.w_hat)[o] = v;
-            else ((__nv_bfloat16*)d.w_hat)[o] = __float2bfloat16_rn(v);
-        }
-    }
+    emit_row(d, d.layout, d.w_hat, w, row, scale);
+    if (d.w_hat2) emit_row(d, d.layout2, d.w_hat2, w, row, scale);
 }
 
 // gradient through w_hat = w * s / (eps + a*||w||),  s = gain*a,  a = 1/sqrt(fan_in):
@@ -100,8 +119,59 @@ wprep_bwd_kernel(const float* __restrict__ w, const float* __restrict__ g, const
     if (d_gain && threadIdx.x == 0) atomicAdd(d_gain, wg * a / den);
 }
 
+// multi-tensor variant; d_w_hat may be in the tap-major layout the weight-gradient kernel accumulates
+__global__ void __launch_bounds__(kWprepThreads)
+wprep_bwd_multi_kernel(const hdmoe_wprep_bwd_desc* __restrict__ descs, int n) {
+    __shared__ float red[kWprepThreads / 32];
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const hdmoe_wprep_bwd_desc d = descs[lo];
+    const int row = blockIdx.x - d.block_start;
+    if (row >= d.rows) return;
+    const float* wr = d.w + (size_t)row * d.fan_in;
+    auto g_at = [&](int i) -> float {
+        if (d.layout == HDMOE_WLAYOUT_SAME) return d.d_w_hat[(size_t)row * d.fan_in + i];
+        const int c = i / d.taps, tap = i - c * d.taps;      // master index i = c*taps + tap
+        return d.d_w_hat[((size_t)tap * d.rows + row) * d.cin_pad + c];
+    };
+    const float a = rsqrtf((float)d.fan_in);
+    float ss = 0.f, wg = 0.f;
+    for (int i = threadIdx.x; i < d.fan_in; i += kWprepThreads) {
+        const float v = wr[i];
+        ss += v * v;
+        wg += v * g_at(i);
+    }
+    const float nrm = sqrtf(block_sum(ss, red));
+    wg = block_sum(wg, red);
+    const float gn = d.gain_ptr ? *d.gain_ptr : d.gain;
+    const float den = kEps + a * nrm;
+    const float s = gn * a / den;
+    const float k = nrm > 0.f ? a * wg / (nrm * den) : 0.f;
+    for (int i = threadIdx.x; i < d.fan_in; i += kWprepThreads) d.d_w[(size_t)row * d.fan_in + i] = s * (g_at(i) - wr[i] * k);
+    if (d.d_gain && threadIdx.x == 0) atomicAdd(d.d_gain, wg * a / den);
+}
+
 }  // namespace hdmoe
 using namespace hdmoe;
+
+extern "C" int hdmoe_wprep_bwd_multi(hdmoe_wprep_bwd_desc* descs_host, void* descs_dev, int n, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(descs_host && descs_dev && n >= 1, "wprep_bwd_multi: null descriptor table");
+    cudaStream_t st = (cudaStream_t)stream;
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        hdmoe_wprep_bwd_desc& d = descs_host[i];
+        HDMOE_CHECK_ARG(d.w && d.d_w_hat && d.d_w && d.rows >= 1 && d.fan_in >= 1, "wprep_bwd_multi: descriptor %d is empty", i);
+        d.block_start = total;
+        total += d.rows;
+    }
+    HDMOE_CHECK_CUDA(cudaMemcpyAsync(descs_dev, descs_host, (size_t)n * sizeof(hdmoe_wprep_bwd_desc), cudaMemcpyHostToDevice, st));
+    wprep_bwd_multi_kernel<<<total, kWprepThreads, 0, st>>>((const hdmoe_wprep_bwd_desc*)descs_dev, n);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
 
 extern "C" int hdmoe_wprep_fwd(hdmoe_wprep_desc* descs_host, void* descs_dev, int n, int force, hdmoe_stream_t stream) {
     HDMOE_CHECK_ARG(descs_host && descs_dev && n >= 1, "wprep_fwd: null descriptor table");
@@ -110,8 +180,11 @@ extern "C" int hdmoe_wprep_fwd(hdmoe_wprep_desc* descs_host, void* descs_dev, in
     for (int i = 0; i < n; ++i) {
         hdmoe_wprep_desc& d = descs_host[i];
         HDMOE_CHECK_ARG(d.w && d.w_hat && d.rows >= 1 && d.fan_in >= 1, "wprep_fwd: descriptor %d is empty", i);
-        if (d.layout == HDMOE_WLAYOUT_TAPS)
+        if (d.layout == HDMOE_WLAYOUT_TAPS || (d.w_hat2 && d.layout2 == HDMOE_WLAYOUT_TAPS))
             HDMOE_CHECK_ARG(d.cin * d.taps == d.fan_in && d.cin_pad >= d.cin, "wprep_fwd: descriptor %d: bad tap layout", i);
+        if (d.layout == HDMOE_WLAYOUT_TAPS_T || (d.w_hat2 && d.layout2 == HDMOE_WLAYOUT_TAPS_T))
+            HDMOE_CHECK_ARG(d.cin * d.taps == d.fan_in && d.cin_rows >= 1 && d.cin_rows <= d.cin && d.cout_pad >= d.rows,
+                            "wprep_fwd: descriptor %d: bad transposed tap layout", i);
         d.block_start = total;
         total += d.rows;
     }

@@ -375,17 +375,21 @@ def edm_heun_correct(x_hat, x_next, x_in_next, F, F_guide, guidance: float, t_ha
 # ----------------------------------------------------------------------------------------------------
 # (5) W-PREP
 # ----------------------------------------------------------------------------------------------------
+_LAYOUTS = {"same": L.WLAYOUT_SAME, "taps": L.WLAYOUT_TAPS, "taps_t": L.WLAYOUT_TAPS_T}
+
+
 class WeightPrep:
-    """Multi-tensor weight preparation plan: one launch normalises / scales / casts many MP_Conv weights."""
+    """Multi-tensor weight preparation plan: ONE launch normalises / scales / casts many MP_Conv weights
+    (include/hdmoe_b200.h §5).  entries: list of dicts with keys
+        w: fp32 Parameter [rows, ...];  out: Tensor (layout `layout`);  out2 / layout2: optional second output;
+        gain: float | 0-dim CUDA tensor;  layout: 'same' | 'taps' | 'taps_t';  cin_pad / cin_rows / cout_pad;
+        active: optional int32 CUDA tensor (1 element): skip the in-place rewrite when it is 0."""
 
     def __init__(self, entries, device):
-        """entries: list of dicts {w: Parameter [rows, ...], out: Tensor, gain: float | Tensor,
-        layout: 'same' | 'taps', cin_pad: int}"""
         self.n = len(entries)
         self.entries = entries
         self.descs = (L.WprepDesc * self.n)()
         self.dev_buf = torch.empty(self.n * C.sizeof(L.WprepDesc), dtype=torch.uint8, device=device)
-        self._fill()
 
     def _fill(self):
         for d, e in zip(self.descs, self.entries):
@@ -394,23 +398,62 @@ class WeightPrep:
             rows = w.shape[0]
             fan_in = w[0].numel()
             taps = 1
-            for s in w.shape[2:]:
-                taps *= s
+            for s_ in w.shape[2:]:
+                taps *= s_
             cin = fan_in // taps
             g = e.get("gain", 1.0)
             d.w, d.w_hat = w.data_ptr(), out.data_ptr()
+            out2 = e.get("out2")
+            d.w_hat2 = out2.data_ptr() if out2 is not None else None
             if torch.is_tensor(g):
                 d.gain_ptr, d.gain = g.data_ptr(), 0.0
             else:
                 d.gain_ptr, d.gain = None, float(g)
+            act = e.get("active")
+            d.active = act.data_ptr() if act is not None else None
             d.rows, d.fan_in, d.cin, d.taps = rows, fan_in, cin, taps
             d.cin_pad = int(e.get("cin_pad", cin))
+            d.cin_rows = int(e.get("cin_rows", cin))
+            d.cout_pad = int(e.get("cout_pad", rows))
             d.out_dtype = _dt(out)
-            d.layout = L.WLAYOUT_TAPS if e.get("layout", "same") == "taps" else L.WLAYOUT_SAME
+            d.layout = _LAYOUTS[e.get("layout", "same")]
+            d.layout2 = _LAYOUTS[e.get("layout2", "same")]
 
     def run(self, force: bool):
         self._fill()      # pointers may have moved (optimizer swaps, .to())
         L.check(L.lib().hdmoe_wprep_fwd(self.descs, _p(self.dev_buf), self.n, int(bool(force)), _st()), "wprep_fwd")
+
+
+class WeightPrepBackward:
+    """ONE launch turning accumulated d_w_hat buffers into master-weight gradients.  entries: dicts with
+    w, d_w_hat (fp32, layout 'same' or 'taps'), d_w (fp32 out), gain (float | tensor), d_gain (optional 0-dim
+    fp32 tensor, accumulated), cin_pad."""
+
+    def __init__(self, entries, device):
+        self.n = len(entries)
+        self.entries = entries
+        self.descs = (L.WprepBwdDesc * self.n)()
+        self.dev_buf = torch.empty(self.n * C.sizeof(L.WprepBwdDesc), dtype=torch.uint8, device=device)
+
+    def run(self):
+        for d, e in zip(self.descs, self.entries):
+            w = e["w"]
+            rows, fan_in = w.shape[0], w[0].numel()
+            taps = 1
+            for s_ in w.shape[2:]:
+                taps *= s_
+            g = e.get("gain", 1.0)
+            d.w, d.d_w_hat, d.d_w = w.data_ptr(), e["d_w_hat"].data_ptr(), e["d_w"].data_ptr()
+            if torch.is_tensor(g):
+                d.gain_ptr, d.gain = g.data_ptr(), 0.0
+            else:
+                d.gain_ptr, d.gain = None, float(g)
+            dg = e.get("d_gain")
+            d.d_gain = dg.data_ptr() if dg is not None else None
+            d.rows, d.fan_in, d.cin, d.taps = rows, fan_in, fan_in // taps, taps
+            d.cin_pad = int(e.get("cin_pad", fan_in // taps))
+            d.layout = _LAYOUTS[e.get("layout", "same")]
+        L.check(L.lib().hdmoe_wprep_bwd_multi(self.descs, _p(self.dev_buf), self.n, _st()), "wprep_bwd_multi")
 
 
 def wprep_bwd(w, d_w_hat, gain):
@@ -424,3 +467,27 @@ def wprep_bwd(w, d_w_hat, gain):
     L.check(L.lib().hdmoe_wprep_bwd(_p(w2), _p(g2), _p(gt), 0.0 if gt is not None else float(gain), w2.shape[0],
                                     w2.shape[1], _p(d_w), _p(d_gain), _st()), "wprep_bwd")
     return d_w.reshape(w.shape), d_gain
+
+
+# ----------------------------------------------------------------------------------------------------
+# (6) grouped implicit-GEMM convolution (tcgen05)
+# ----------------------------------------------------------------------------------------------------
+def gconv_raw(x, w_cat, cout: int, w_rows_total: int, row_expert, n_rows_dev, ksizes, wrows, scale=None,
+              act: int = 0, residual=None, res_a: float = 0.0, res_b: float = 1.0):
+    """y[cap,H,W,cout] = grouped 'same' conv of NHWC bf16 x with the tap-major prepared weights of each row's
+    expert, fused epilogue out = res_a*residual + res_b*act(scale*conv)."""
+    _cuda(x, w_cat)
+    assert x.dtype == torch.bfloat16 and w_cat.dtype == torch.bfloat16 and x.is_contiguous() and w_cat.is_contiguous()
+    cap, H, W, cin_pad = x.shape
+    E = len(ksizes)
+    y = torch.empty(cap, H, W, cout, dtype=torch.bfloat16, device=x.device)
+    ks = (C.c_int32 * E)(*ksizes)
+    wr = (C.c_int32 * E)(*wrows)
+    if scale is not None:
+        scale = _f32c(scale)
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == y.shape
+    L.check(L.lib().hdmoe_gconv_fwd(_p(x), _p(w_cat), _p(y), cap, H, W, cin_pad, cout, w_rows_total, _p(row_expert),
+                                    _p(n_rows_dev), E, ks, wr, _p(scale), int(act), _p(residual), float(res_a),
+                                    float(res_b), _st()), "gconv_fwd")
+    return y

@@ -161,19 +161,25 @@ int hdmoe_edm_heun_correct(const float* x_hat, const float* x_next, const void* 
  *        force != 0 (training):  w[o,:] <- w[o,:] / (eps + ||w[o,:]|| / sqrt(fan_in))     (in place, Q6)
  *        w_hat[o,:] = w[o,:] / (eps + ||w[o,:]|| / sqrt(fan_in)) * gain / sqrt(fan_in)
  *     Output layout HDMOE_WLAYOUT_SAME keeps [rows][fan_in]; HDMOE_WLAYOUT_TAPS writes the implicit-GEMM
- *     layout [tap][rows][cin_pad] (K-major, zero padded) consumed by hdmoe_grouped_conv_fwd.
+ *     layout [tap][rows][cin_pad] (K-major, zero padded) consumed by hdmoe_gconv_fwd; HDMOE_WLAYOUT_TAPS_T the
+ *     transposed, tap-flipped operand with which the same kernel computes the data gradient.
  * ---------------------------------------------------------------------------------------------- */
 #define HDMOE_WLAYOUT_SAME 0
 #define HDMOE_WLAYOUT_TAPS 1
+#define HDMOE_WLAYOUT_TAPS_T 2  /* data-gradient operand: [taps-1-tap][cin_rows][cout_pad] (transposed, flipped)    */
 typedef struct {
-    float* w;               /* [rows][fan_in] fp32 master weights (mutated when force != 0)         */
-    void* w_hat;            /* output                                                                */
-    const float* gain_ptr;  /* optional device scalar gain (e.g. Unet_expert.out_gain); NULL -> gain */
+    float* w;               /* [rows][fan_in] fp32 master weights (mutated when force != 0)                   */
+    void* w_hat;            /* output 1                                                                        */
+    void* w_hat2;           /* optional output 2 (layout2), NULL to skip                                       */
+    const float* gain_ptr;  /* optional device scalar gain (e.g. Unet_expert.out_gain); NULL -> gain           */
+    const int32_t* active;  /* optional device flag: the in-place rewrite is skipped when *active == 0 (an     */
+                            /* expert that received no rows does not run MP_Conv.forward in the reference)     */
     float gain;
-    int32_t rows, fan_in;   /* fan_in = cin * taps                                                   */
-    int32_t cin, taps, cin_pad;
-    int32_t out_dtype, layout;
-    int32_t block_start;    /* filled by the callee's host wrapper: first CTA of this tensor        */
+    int32_t rows, fan_in;   /* fan_in = cin * taps                                                             */
+    int32_t cin, taps, cin_pad;   /* TAPS: inner dim padded to cin_pad                                         */
+    int32_t cin_rows, cout_pad;   /* TAPS_T: cin_rows (<= cin) rows per tap, inner dim padded to cout_pad       */
+    int32_t out_dtype, layout, layout2;
+    int32_t block_start;    /* filled by the host wrapper: first CTA of this tensor                            */
 } hdmoe_wprep_desc;
 /* descs: HOST array of n descriptors (copied to `descs_dev`, a device buffer of n*sizeof(desc) bytes). */
 int hdmoe_wprep_fwd(hdmoe_wprep_desc* descs_host, void* descs_dev, int n, int force, hdmoe_stream_t stream);
@@ -181,6 +187,19 @@ int hdmoe_wprep_fwd(hdmoe_wprep_desc* descs_host, void* descs_dev, int n, int fo
  * models/model_internals.py:258-259).  d_gain (device scalar, accumulated) may be NULL. */
 int hdmoe_wprep_bwd(const float* w, const float* d_w_hat, const float* gain_ptr, float gain, int rows, int fan_in,
                     float* d_w, float* d_gain, hdmoe_stream_t stream);
+/* Multi-tensor backward: one launch for n weights.  d_w_hat is fp32 in layout SAME ([rows][fan_in]) or TAPS
+ * ([tap][rows][cin_pad], what the weight-gradient kernel accumulates); d_w is written in the master layout. */
+typedef struct {
+    const float* w;
+    const float* d_w_hat;
+    const float* gain_ptr;
+    float* d_w;
+    float* d_gain;          /* optional, accumulated with atomicAdd */
+    float gain;
+    int32_t rows, fan_in, cin, taps, cin_pad, layout;
+    int32_t block_start;
+} hdmoe_wprep_bwd_desc;
+int hdmoe_wprep_bwd_multi(hdmoe_wprep_bwd_desc* descs_host, void* descs_dev, int n, hdmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (6) Grouped implicit-GEMM convolution / GEMM on tcgen05 + TMEM + TMA -- replaces the F.conv2d /

@@ -20,7 +20,7 @@ extern "C" {
  *   ksize_host / wrow_host: HOST arrays of length n_experts.
  * Fused epilogue:  v = acc * scale[row, c] (scale may be NULL);  v = mp_silu(v) if act == 1;
  *                  out = res_a * residual + res_b * v  if residual != NULL  (mp_sum folded).
- * Constraints: Cout in {32, 64, 128}; Cin_pad % 32 == 0; W | 128; 128 | H*W. */
+ * Constraints: Cout in {32, 64, 96, 128}; Cin_pad % 32 == 0; W | 128; 128 | H*W. */
 int hdmoe_gconv_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H, int W, int Cin_pad, int Cout,
                     int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev, int n_experts,
                     const int32_t* ksize_host, const int32_t* wrow_host, const float* scale, int act,

@@ -477,3 +477,67 @@ def test_sampler_golden(case):
         torch.randn_like = orig
     assert smp.nfe == (2 * g["meta.num_steps"] - 1) * (2 if g["meta.guidance"] != 1.0 else 1)
     assert rel_l2(out.cpu(), g["out.x"]) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ grouped experts
+@pytest.mark.parametrize("train", [False, True])
+def test_grouped_tcgen05_unet_experts_match_per_expert_path(train):
+    """The grouped tcgen05 expert path (all U-Net experts per layer in one launch) against (a) the per-expert
+    bf16 path built from stock ops and (b) the fp32 oracle: outputs, input gradient, parameter gradients."""
+    import hdmoe_b200
+    from hdmoe_b200.utils import EDM_LOSS
+    model, sd = _full_model_pair(2)
+    model.cuda().train(train)
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if hasattr(mod, "dropout") and not isinstance(mod, torch.nn.Dropout):
+            mod.dropout = 0
+    B = 16
+    x0, sigma, x, text = _full_inputs(B, 32)
+    ones = torch.ones(B, 4)
+    gen = torch.Generator().manual_seed(3)
+    noise = {"vit": torch.randn(B, 4, generator=gen).cuda(), "unet": torch.randn(B, 4, generator=gen).cuda()}
+    crit = EDM_LOSS(num_experts=4, sigma_data=0.5, Unet_bal=0.05, vit_bal=0.1, z_bal=0.005, prior_bal=0.0)
+    res = {}
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    hdmoe_b200.set_expert_dtype(torch.bfloat16)
+    try:
+        for mode in ("grouped", "loop"):
+            hdmoe_b200.set_grouped_experts(mode == "grouped")
+            model.load_state_dict(state0)
+            model.zero_grad(set_to_none=True)
+            xin = x.cuda().requires_grad_(True)
+            out = model(x=xin, sigma=sigma.cuda(), text_emb=text.cuda(), Unet_router_mask=ones.cuda(),
+                        Vit_router_mask=ones.cuda(), zeta=0.5, transition_point=-1.2, softness=1.6,
+                        return_log_var=True, noise=noise)
+            if train:
+                crit(sigma.cuda(), x0.cuda(), sigma.cuda(), out)["loss"].backward()
+            res[mode] = dict(out=out["denoised"].detach().float().cpu(),
+                             gx=xin.grad.cpu() if train else None,
+                             gp={n: p.grad.detach().float().cpu() for n, p in model.named_parameters()
+                                 if train and p.grad is not None and "Unet_experts" in n},
+                             w={n: p.detach().float().cpu() for n, p in model.named_parameters() if "Unet_experts.2" in n})
+    finally:
+        hdmoe_b200.set_expert_dtype(torch.float32)
+        hdmoe_b200.set_grouped_experts(True)
+    assert rel_l2(res["grouped"]["out"], res["loop"]["out"]) < 2e-2
+    with torch.no_grad():
+        import contextlib
+        sd_o = {k: v.clone() for k, v in sd.items()}
+        with (O.training_mode() if train else contextlib.nullcontext()):
+            ref = O.preconditioned(sd_o, FULL, x, sigma, text, ones, ones, 0.5, -1.2, 1.6, variant=2,
+                                   noise={k: v.cpu() for k, v in noise.items()} if train else None)
+    assert rel_l2(res["grouped"]["out"], ref["denoised"]) < TOLBF
+    if train:
+        assert rel_l2(res["grouped"]["gx"], res["loop"]["gx"]) < 5e-2
+        checked = 0
+        for n, g in res["loop"]["gp"].items():
+            if float(g.abs().max()) == 0:
+                continue
+            assert n in res["grouped"]["gp"], n
+            assert rel_l2(res["grouped"]["gp"][n], g) < 8e-2, n      # bf16 activations on both sides
+            checked += 1
+        assert checked > 150
+        for n, w in res["loop"]["w"].items():                        # forced weight norm applied identically (Q6)
+            assert rel_l2(res["grouped"]["w"][n], w) < 1e-5, n
