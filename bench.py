@@ -244,7 +244,9 @@ def run_ours(args):
     line = None
     if rank == 0:
         peaks = load_peaks()
-        roof = roofline_dispatch(device, peaks, flush)
+        roof = roofline_gconv(device, peaks, flush)
+        disp = dispatch_sweep(device, peaks, flush, full=args.full_sweep)
+        samp = sampler_throughput(device) if not args.no_sampler else None
         cpu = cpu_baseline_train(sample_batch=8, iters=3)
         line = {"metric": "denoiser train img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
@@ -258,7 +260,8 @@ def run_ours(args):
                 "e2e": {"value": round(e2e_value, 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3), "last_loss": loss_host},
                 "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "peaks": peaks["src"]}
+                "roofline": roof, "cpu_baseline": cpu, "peaks": peaks["src"],
+                "dispatch": disp, "sampler": samp}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -266,38 +269,98 @@ def run_ours(args):
     return line
 
 
-def roofline_dispatch(device, peaks, flush, T=256, E=4, D=32 * 32 * 32, iters=20):
-    """Dominant hand-written kernel of the current step: the MoE row gather + gate-weighted combine at the
-    training shape (256 rows of 32x32x32 bf16 = 64 KiB).  achieved = algorithmic bytes / CUDA-event time."""
-    from hdmoe_b200 import ops
-    gen = torch.Generator(device="cpu").manual_seed(3)
-    lg = torch.randn(T, E, generator=gen)
-    sp = torch.zeros(T, E).scatter_(1, lg.argmax(1, keepdim=True), 1.0).to(device)
-    x = torch.randn(T, D, generator=gen).to(device=device, dtype=torch.bfloat16)
-    plan = ops.dispatch_plan(sp, top_k=1)
-    rows = ops.permute(plan, x)[0]
-    out = ops.combine(rows, sp, plan)
-    tp = tc = 0.0
-    for i in range(iters + 3):
+def _time_us(fn, flush, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    tot = 0.0
+    for _ in range(iters):
         flush()
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        rows = ops.permute(plan, x)[0]
+        fn()
         b.record()
-        out = ops.combine(rows, sp, plan)
-        c.record()
         torch.cuda.synchronize()
-        if i >= 3:
-            tp += a.elapsed_time(b)
-            tc += b.elapsed_time(c)
-    R, s = T, 2
-    bytes_p = 2 * R * D * s + R * 4                     # SURVEY §8d: rows read + written + index
-    bytes_c = R * D * s + R * 8 + T * D * s
-    ach = (bytes_p + bytes_c) / ((tp + tc) / iters * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "permute_bulk_kernel + combine_kernel (T=256, 64 KiB bf16 rows)",
-            "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4),
-            "traffic": None, "permute_us": round(tp / iters * 1e3, 2), "combine_us": round(tc / iters * 1e3, 2),
-            "algorithmic_bytes": bytes_p + bytes_c}
+        tot += a.elapsed_time(b)
+    return tot / iters * 1e3
+
+
+def dispatch_point(device, flush, T, E, k, D, iters=10, dtype=torch.bfloat16):
+    """permute + combine at one (tokens, experts, top-k, row width) point; algorithmic bytes per SURVEY §8d."""
+    from hdmoe_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(T + E + k)
+    lg = torch.randn(T, E, generator=gen) + torch.log(1.0 / torch.arange(1, E + 1).float())     # Zipf-skewed load
+    idx = lg.topk(k, dim=1).indices
+    sp = torch.zeros(T, E).scatter_(1, idx, 1.0 / k).to(device)
+    x = torch.randn(T, D, generator=gen).to(device=device, dtype=dtype)
+    plan = ops.dispatch_plan(sp, top_k=k)
+    rows = ops.permute(plan, x)[0]
+    s = x.element_size()
+    R = T * k
+    t_plan = _time_us(lambda: ops.dispatch_plan(sp, top_k=k), flush, iters)
+    t_perm = _time_us(lambda: ops.permute(plan, x), flush, iters)
+    t_comb = _time_us(lambda: ops.combine(rows, sp, plan), flush, iters)
+    b_perm = 2 * R * D * s + R * 4
+    b_comb = R * D * s + R * 8 + T * D * s
+    return {"T": T, "E": E, "k": k, "row_bytes": D * s, "plan_us": round(t_plan, 1), "permute_us": round(t_perm, 1),
+            "combine_us": round(t_comb, 1), "permute_GBs": round(b_perm / t_perm / 1e3, 1),
+            "combine_GBs": round(b_comb / t_comb / 1e3, 1),
+            "dispatch_combine_GBs": round((b_perm + b_comb) / (t_perm + t_comb) / 1e3, 1)}
+
+
+def dispatch_sweep(device, peaks, flush, full=False):
+    pts = [(1024, 4, 1, 32768), (1024, 8, 2, 32768), (65536, 16, 2, 512), (262144, 64, 2, 128), (1048576, 64, 1, 128)]
+    if full:
+        pts = [(T, E, k, D) for T in (4096, 16384, 65536, 262144, 1048576) for E in (4, 8, 16, 32, 64) for k in (1, 2)
+               for D in (32, 128, 512) if T * k * D * 2 <= (4 << 30)] + [(256, 4, 1, 32768), (1024, 4, 1, 32768)]
+    out = [dispatch_point(device, flush, *p) for p in pts]
+    best = max(o["dispatch_combine_GBs"] for o in out)
+    return {"unit": "GB/s", "peak": peaks["hbm"], "best_frac": round(best / peaks["hbm"], 4), "points": out}
+
+
+def roofline_gconv(device, peaks, flush, iters=10):
+    """Dominant hand-written kernel of the train step by FLOPs: the tcgen05 grouped implicit-GEMM convolution.
+    Shape: the most frequent U-Net expert layer at the bench batch (256 rows routed 36/48/75/97 to the 3x3,
+    3x3, 5x5, 5x5 experts), 32x32, Cin = Cout = 64.  flops = sum_e 2*n_e*H*W*Cout*Cin*k_e^2."""
+    from hdmoe_b200 import ops
+    counts, ks = [36, 48, 75, 97], [3, 3, 5, 5]
+    R, H, Cin, Cout = sum(counts), 32, 64, 64
+    row_e = torch.tensor(sum(([e] * c for e, c in enumerate(counts)), []), dtype=torch.int32, device=device)
+    n_rows = torch.tensor([R], dtype=torch.int32, device=device)
+    x = torch.randn(R, H, H, Cin, device=device).to(torch.bfloat16)
+    wrow, tot = [], 0
+    for k in ks:
+        wrow.append(tot)
+        tot += k * k * Cout
+    w = (torch.randn(tot, Cin, device=device) / 30).to(torch.bfloat16)
+    us = _time_us(lambda: ops.gconv_raw(x, w, Cout, tot, row_e, n_rows, ks, wrow), flush, iters)
+    flops = sum(2.0 * c * H * H * Cout * Cin * k * k for c, k in zip(counts, ks))
+    ach = flops / us / 1e6
+    return {"bound": "tensor", "kernel": "gconv_fwd_kernel<64,64> (256 rows 32x32, Cin=Cout=64, k=3,3,5,5 routed 36/48/75/97)",
+            "achieved": round(ach, 1), "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": round(ach / peaks["bf16"], 4),
+            "traffic": None, "us_per_launch": round(us, 1), "algorithmic_flops": flops,
+            "peak_basis": "burst (kernel timed alone), " + peaks["src"]}
+
+
+def sampler_throughput(device, B=1024, steps=18):
+    """EDM Heun sampler, 18 steps / 35 NFE, model_config2, CLIP-shaped text (BASELINE.json configs[3])."""
+    import hdmoe_b200
+    model = build_model(2, device)
+    model.eval()
+    gen = torch.Generator().manual_seed(SEED)
+    noise = torch.randn(B, 4, 32, 32, generator=gen).to(device)
+    text = torch.randn(B, 77, 768, generator=gen).to(device)
+    smp = hdmoe_b200.EDM_Sampler(model, model, num_solve_steps=steps, guidance=1.0)
+    smp.sample(noise[:64], text[:64], P_MEAN, P_STD)     # warm-up (allocator, autotune)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    smp.nfe = 0
+    a.record()
+    out = smp.sample(noise, text, P_MEAN, P_STD)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    return {"metric": "EDM sample img/s", "value": round(B / (ms / 1e3), 1), "unit": "img/s", "batch": B, "nfe": smp.nfe,
+            "ms": round(ms, 1), "finite": bool(torch.isfinite(out).all())}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -365,6 +428,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--profile-step", action="store_true", help="cudaProfilerStart/Stop around the first timed step")
+    ap.add_argument("--full-sweep", action="store_true", help="full MoE dispatch/combine sweep (BASELINE configs[4])")
+    ap.add_argument("--no-sampler", action="store_true", help="skip the EDM sampler throughput extra")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

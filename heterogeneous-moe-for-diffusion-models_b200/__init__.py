@@ -7,7 +7,9 @@ Importing the package does not need a GPU; calling any op does, and a missing li
 """
 from . import _lib, ops  # noqa: F401
 from . import model_internals, model_components, model_config1, model_config2, EDM_sampler, utils  # noqa: F401
-from ._denoiser import get_expert_dtype, set_expert_dtype, set_grouped_experts  # noqa: F401
+from . import expert_parallel  # noqa: F401
+from ._denoiser import (disable_expert_parallel, enable_expert_parallel, get_expert_dtype,  # noqa: F401
+                        set_expert_dtype, set_grouped_experts)
 from .EDM_sampler import EDM_Sampler  # noqa: F401
 
 __all__ = ["ops", "model_internals", "model_components", "model_config1", "model_config2", "EDM_sampler", "utils",

@@ -33,6 +33,48 @@ def set_grouped_experts(enabled: bool) -> None:
     _GROUPED[0] = bool(enabled)
 
 
+# expert parallelism for the U-Net MoE layer; None = every rank runs all experts (pure DP)
+_EP = {"placement": None, "group": None}
+
+
+def enable_expert_parallel(kernel_sizes=None, group=None, placement=None) -> None:
+    """Shard the U-Net experts over the ranks of `group` (cost-balanced); ViT experts stay replicated."""
+    import torch.distributed as dist
+    from . import expert_parallel as EP
+    if placement is None:
+        placement = EP.ExpertPlacement.balanced(EP.unet_expert_costs(kernel_sizes), dist.get_world_size(group))
+    _EP["placement"], _EP["group"] = placement, group
+
+
+def disable_expert_parallel() -> None:
+    _EP["placement"] = _EP["group"] = None
+
+
+def _run_experts_on_rows(experts, plan, xr, tr, txr):
+    """experts on expert-major rows: grouped tcgen05 path when possible, per-expert loop otherwise."""
+    if (xr.dtype == torch.bfloat16 and _GROUPED[0] and len(experts) > 0
+            and all(isinstance(ex, mc.Unet_expert) for ex in experts) and _groupable(experts, xr)):
+        from .grouped import GroupedUnetExperts
+        holder = experts.__dict__ if isinstance(experts, nn.ModuleList) else experts[0].__dict__
+        key = "_hdmoe_grouped_" + "_".join(str(id(e)) for e in experts)
+        runner = holder.get(key)
+        if runner is None:
+            runner = GroupedUnetExperts(experts)
+            holder[key] = runner
+        return runner(plan, xr, tr, txr, training=experts[0].training).contiguous()
+    off = plan.host_offsets()
+    outs = []
+    for e, expert in enumerate(experts):
+        lo, hi = off[e], off[e + 1]
+        if hi == lo:
+            continue
+        outs.append(expert(x=xr[lo:hi], time_emb=tr[lo:hi], text_emb=None if txr is None else txr[lo:hi]))
+    R = off[-1]
+    if R < plan.cap:   # unused tail rows (tokens dispatched to fewer than K experts)
+        outs.append(xr.new_zeros((plan.cap - R,) + tuple(xr.shape[1:])))
+    return torch.cat(outs, dim=0) if len(outs) != 1 else outs[0]
+
+
 def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: torch.Tensor,
                            time_emb: torch.Tensor, text_emb: Optional[torch.Tensor],
                            top_k: Optional[int] = None) -> torch.Tensor:
@@ -45,31 +87,21 @@ def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: 
     if text_emb is not None and text_emb.ndim == 3:
         text_emb = text_emb.mean(dim=1)
     dt = get_expert_dtype()
+    if _EP["placement"] is not None and all(isinstance(ex, mc.Unet_expert) for ex in experts):
+        from . import expert_parallel as EP
+        k = out_router.shape[1] if top_k is None else top_k
+
+        def run_local(local_ids, lplan, xr_, tr_, txr_):
+            return _run_experts_on_rows([experts[i] for i in local_ids], lplan, xr_, tr_, txr_)
+
+        return EP.ep_moe_layer(x, out_router, time_emb, text_emb, run_local, _EP["placement"], k, group=_EP["group"],
+                               payload_dtype=dt)
     plan = ops.dispatch_plan(out_router, top_k)
     srcs = [x.to(dt), time_emb.to(dt)] + ([text_emb.to(dt)] if text_emb is not None else [])
     rows = ops.permute(plan, *srcs)
     xr, tr = rows[0], rows[1]
     txr = rows[2] if text_emb is not None else None
-    if (dt == torch.bfloat16 and _GROUPED[0] and len(experts) > 0
-            and all(isinstance(ex, mc.Unet_expert) for ex in experts) and _groupable(experts, xr)):
-        from .grouped import GroupedUnetExperts
-        runner = experts.__dict__.get("_hdmoe_grouped")
-        if runner is None:
-            runner = GroupedUnetExperts(experts)
-            experts.__dict__["_hdmoe_grouped"] = runner
-        out_rows = runner(plan, xr, tr, txr, training=experts[0].training)
-        return ops.combine(out_rows.contiguous(), out_router, plan, base=None, out_dtype=x.dtype)
-    off = plan.host_offsets()
-    outs = []
-    for e, expert in enumerate(experts):
-        lo, hi = off[e], off[e + 1]
-        if hi == lo:
-            continue
-        outs.append(expert(x=xr[lo:hi], time_emb=tr[lo:hi], text_emb=None if txr is None else txr[lo:hi]))
-    R = off[-1]
-    if R < plan.cap:   # unused tail rows (tokens dispatched to fewer than K experts)
-        outs.append(xr.new_zeros((plan.cap - R,) + tuple(xr.shape[1:])))
-    out_rows = torch.cat(outs, dim=0) if len(outs) != 1 else outs[0]
+    out_rows = _run_experts_on_rows(experts, plan, xr, tr, txr)
     return ops.combine(out_rows, out_router, plan, base=None, out_dtype=x.dtype)
 
 
