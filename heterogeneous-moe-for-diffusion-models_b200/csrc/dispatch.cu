@@ -19,23 +19,47 @@ namespace hdmoe {
 // ---------------------------------------------------------------------------------------------------
 constexpr int kPlanThreads = 256;
 
-__device__ __forceinline__ unsigned long long token_mask(const float* __restrict__ w, int t, int T, int E) {
-    unsigned long long m = 0ull;
-    if (t < T) {
-        const float* r = w + (size_t)t * E;
-        for (int e = 0; e < E; ++e)
-            if (__ldg(r + e) > 0.f) m |= 1ull << e;   // NaN > 0 is false (quirk Q3)
+// Selection flags of one 256-token tile, built with COALESCED loads: warp-wide 32-element reads of the dense
+// [T, E] matrix are turned into bit words with __ballot_sync (sparse_w > 0; NaN > 0 is false, quirk Q3) and
+// parked in shared memory; each thread then extracts the E bits of its own token.
+__device__ __forceinline__ unsigned long long token_mask(const float* __restrict__ w, int tile, int T, int E,
+                                                         uint32_t* bits /* [kPlanThreads*64/32 + 2] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long base = (long long)tile * kPlanThreads * E;
+    const int ntok = min(kPlanThreads, T - tile * kPlanThreads);
+    const int nelem = ntok * E;
+    const int nwords = (kPlanThreads * E + 31) / 32;
+    // 8 independent 128-byte loads in flight per warp before the ballots (the loop is latency-bound otherwise)
+    constexpr int kU = 8, kW = kPlanThreads / 32;
+    for (int w0 = warp * kU; w0 < nwords + 2; w0 += kW * kU) {
+        float v[kU];
+#pragma unroll
+        for (int q = 0; q < kU; ++q) {
+            const int idx = (w0 + q) * 32 + lane;
+            v[q] = idx < nelem ? __ldg(w + base + idx) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < kU; ++q) {
+            const unsigned b = __ballot_sync(0xffffffffu, v[q] > 0.f);
+            if (lane == 0 && w0 + q < nwords + 2) bits[w0 + q] = b;
+        }
     }
-    return m;
+    __syncthreads();
+    const int o = threadIdx.x * E;
+    const int wd = o >> 5, sh = o & 31;
+    const unsigned long long lo = (unsigned long long)bits[wd] | ((unsigned long long)bits[wd + 1] << 32);
+    unsigned long long v = lo >> sh;
+    if (sh) v |= (unsigned long long)bits[wd + 2] << (64 - sh);
+    if (E < 64) v &= (1ull << E) - 1ull;
+    return threadIdx.x < ntok ? v : 0ull;
 }
 
 __global__ void __launch_bounds__(kPlanThreads)
 plan_count_kernel(const float* __restrict__ w, int T, int E, int ntiles, int32_t* __restrict__ tilecnt) {
     __shared__ int cnt[HDMOE_MAX_EXPERTS];
+    __shared__ uint32_t bits[kPlanThreads * HDMOE_MAX_EXPERTS / 32 + 2];
     if (threadIdx.x < E) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const int t = blockIdx.x * kPlanThreads + threadIdx.x;
-    const unsigned long long m = token_mask(w, t, T, E);
+    const unsigned long long m = token_mask(w, blockIdx.x, T, E, bits);   // contains a __syncthreads
     const int lane = threadIdx.x & 31;
     for (int e = 0; e < E; ++e) {
         const unsigned b = __ballot_sync(0xffffffffu, (m >> e) & 1ull);
@@ -99,8 +123,9 @@ plan_scatter_kernel(const float* __restrict__ w, int T, int E, int ntiles, int c
                     int32_t* __restrict__ row_expert, float* __restrict__ row_w, int32_t* __restrict__ tok_rows,
                     int32_t* __restrict__ status) {
     __shared__ int warpoff[kPlanThreads / 32][HDMOE_MAX_EXPERTS];
+    __shared__ uint32_t bits[kPlanThreads * HDMOE_MAX_EXPERTS / 32 + 2];
     const int t = blockIdx.x * kPlanThreads + threadIdx.x;
-    const unsigned long long m = token_mask(w, t, T, E);
+    const unsigned long long m = token_mask(w, blockIdx.x, T, E, bits);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int e = 0; e < E; ++e) {
         const unsigned b = __ballot_sync(0xffffffffu, (m >> e) & 1ull);
@@ -261,8 +286,41 @@ permute_bulk_kernel(PermuteArgs a, const int32_t* __restrict__ row_src, const in
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// vector path: one warp per (row, tensor, 2 KiB piece)
+// vector path A (16-byte aligned rows): flat over 16-byte vectors, 4 independent loads in flight per thread
 constexpr int kVecPiece = 2048;
+__global__ void __launch_bounds__(256)
+permute_vec16_kernel(PermuteArgs a, const int32_t* __restrict__ row_src, const int32_t* __restrict__ n_rows_dev,
+                     int cap, int vec_per_rowset, int vb1, int vb2, int vb3) {
+    const int R = min(*n_rows_dev, cap);
+    const long long total = (long long)cap * vec_per_rowset;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += 4 * stride) {
+        int4 val[4];
+        int4* dstp[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long v = v0 + q * stride;
+            dstp[q] = nullptr;
+            val[q] = make_int4(0, 0, 0, 0);
+            if (v < total) {
+                const int r = (int)(v / vec_per_rowset);
+                int c = (int)(v - (long long)r * vec_per_rowset);
+                int i = 0;
+                if (a.n_tensors > 3 && c >= vb3) { i = 3; c -= vb3; }
+                else if (a.n_tensors > 2 && c >= vb2) { i = 2; c -= vb2; }
+                else if (a.n_tensors > 1 && c >= vb1) { i = 1; c -= vb1; }
+                dstp[q] = reinterpret_cast<int4*>(a.dst[i] + (long long)r * a.row_bytes[i]) + c;
+                if (r < R)
+                    val[q] = ld_stream(reinterpret_cast<const int4*>(a.src[i] + (long long)row_src[r] * a.row_bytes[i]) + c);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (dstp[q]) st_stream(dstp[q], val[q]);
+    }
+}
+
+// vector path B (rows that are only 4-byte aligned): one warp per (row, tensor, 2 KiB piece)
 __global__ void __launch_bounds__(256)
 permute_vec_kernel(PermuteArgs a, const int32_t* __restrict__ row_src, const int32_t* __restrict__ n_rows_dev,
                    int cap, long long pieces_per_rowset, long long piece_base1, long long piece_base2,
@@ -310,29 +368,94 @@ permute_vec_kernel(PermuteArgs a, const int32_t* __restrict__ row_src, const int
 // ---------------------------------------------------------------------------------------------------
 // Combine.  grid-stride over (token, 4-element vector); K <= 8 gathered rows per token.
 // ---------------------------------------------------------------------------------------------------
+// N-element register vectors: 16 bytes of the ROW dtype per access (8 bf16 / 4 fp32)
+template <typename T>
+struct VecN;
+template <>
+struct VecN<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+        const float4 f = *reinterpret_cast<const float4*>(p);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    }
+};
+template <>
+struct VecN<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const int4 u = ld_stream(reinterpret_cast<const int4*>(p));
+        const uint32_t w[4] = {(uint32_t)u.x, (uint32_t)u.y, (uint32_t)u.z, (uint32_t)u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[2 * q] = __uint_as_float(w[q] << 16);
+            v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+        }
+    }
+};
+template <typename TO, int N>
+__device__ __forceinline__ void store_n(TO* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store_n<float, 4>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void store_n<float, 8>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store_n<__nv_bfloat16, 4>(__nv_bfloat16* p, const float (&v)[8]) {
+    Vec4<__nv_bfloat16>::store(p, make_float4(v[0], v[1], v[2], v[3]));
+}
+template <>
+__device__ __forceinline__ void store_n<__nv_bfloat16, 8>(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        __nv_bfloat162 o = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+        w[q] = *reinterpret_cast<uint32_t*>(&o);
+    }
+    st_stream(reinterpret_cast<int4*>(p), make_int4(w[0], w[1], w[2], w[3]));
+}
+template <typename TO, int N>
+__device__ __forceinline__ void load_base(const TO* p, float (&v)[8]) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) v[q] = to_f32<TO>(p[q]);
+}
+
 template <typename TR, typename TO>
 __global__ void __launch_bounds__(256)
 combine_kernel(const TR* __restrict__ rows, const int32_t* __restrict__ tok_rows, const float* __restrict__ row_w,
-               const TO* __restrict__ base, TO* __restrict__ out, int T, int K, long long D) {
-    const long long vec_per_row = D >> 2;
+               const TO* __restrict__ base, TO* __restrict__ out, int T, int K, long long D, int vshift) {
+    constexpr int N = VecN<TR>::N;
+    const long long vec_per_row = D / N;
     const long long total = (long long)T * vec_per_row;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int t = (int)(i / vec_per_row);
-        const long long d = (i - (long long)t * vec_per_row) << 2;
-        float4 acc = base ? Vec4<TO>::load(base + (long long)t * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j = 0; j < K; ++j) {
-            const int r = tok_rows[(long long)t * K + j];
-            if (r < 0) continue;
-            const float w = row_w ? row_w[r] : 1.f;
-            const float4 v = Vec4<TR>::load(rows + (long long)r * D + d);
-            // multiply, round, then add (the reference does `out_e * w` then `+=`): no FMA contraction
-            acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, w));
-            acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, w));
-            acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, w));
-            acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, w));
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= total) break;
+            const int t = vshift >= 0 ? (int)(i >> vshift) : (int)(i / vec_per_row);
+            const long long d = (i - (long long)t * vec_per_row) * N;
+            float acc[8];
+            if (base) load_base<TO, N>(base + (long long)t * D + d, acc);
+            else {
+#pragma unroll
+                for (int q = 0; q < N; ++q) acc[q] = 0.f;
+            }
+            for (int j = 0; j < K; ++j) {
+                const int r = __ldg(tok_rows + (long long)t * K + j);
+                if (r < 0) continue;
+                const float w = row_w ? __ldg(row_w + r) : 1.f;
+                float v[8];
+                VecN<TR>::load(rows + (long long)r * D + d, v);
+                // multiply, round, then add (the reference does `out_e * w` then `+=`): no FMA contraction
+#pragma unroll
+                for (int q = 0; q < N; ++q) acc[q] = __fadd_rn(acc[q], __fmul_rn(v[q], w));
+            }
+            store_n<TO, N>(out + (long long)t * D + d, acc);
         }
-        Vec4<TO>::store(out + (long long)t * D + d, acc);
     }
 }
 
@@ -447,6 +570,15 @@ extern "C" int hdmoe_permute_rows(const void* const* srcs, void* const* dsts, co
         long long g = total < (long long)kNumSMs * 2 ? total : (long long)kNumSMs * 2;
         permute_bulk_kernel<<<(int)g, 32, smem, st>>>(a, row_src, n_rows_dev, cap, base);
         HDMOE_CHECK_LAUNCH();
+    } else if (bulk_ok && max_row < 1024) {
+        int vb[4] = {0, 0, 0, 0}, base = 0;
+        for (int i = 0; i < n_tensors; ++i) {
+            vb[i] = base;
+            base += (int)(row_bytes[i] / 16);
+        }
+        const long long total = (long long)cap * base;
+        permute_vec16_kernel<<<grid_for(total, 1024, 16), 256, 0, st>>>(a, row_src, n_rows_dev, cap, base, vb[1], vb[2], vb[3]);
+        HDMOE_CHECK_LAUNCH();
     } else {
         long long pb[4] = {0, 0, 0, 0}, base = 0;
         for (int i = 0; i < n_tensors; ++i) {
@@ -463,9 +595,14 @@ extern "C" int hdmoe_permute_rows(const void* const* srcs, void* const* dsts, co
 template <typename TR, typename TO>
 static int launch_combine(const void* rows, const int32_t* tok_rows, const float* row_w, const void* base, void* out,
                           int T, int K, int64_t D, cudaStream_t st) {
-    const long long total = (long long)T * (D >> 2);
-    combine_kernel<TR, TO><<<grid_for(total, 256, 16), 256, 0, st>>>((const TR*)rows, tok_rows, row_w, (const TO*)base,
-                                                                    (TO*)out, T, K, D);
+    constexpr int N = VecN<TR>::N;
+    const long long vpr = D / N;
+    const long long total = (long long)T * vpr;
+    int vshift = -1;
+    for (int b = 0; b < 31; ++b)
+        if ((1ll << b) == vpr) vshift = b;
+    combine_kernel<TR, TO><<<grid_for(total, 512, 16), 256, 0, st>>>((const TR*)rows, tok_rows, row_w, (const TO*)base,
+                                                                    (TO*)out, T, K, D, vshift);
     HDMOE_CHECK_LAUNCH();
     return HDMOE_OK;
 }
@@ -474,8 +611,10 @@ extern "C" int hdmoe_combine_rows(const void* rows, int rows_dtype, const int32_
                                   const void* base, void* out, int out_dtype, int T, int K, int64_t D,
                                   hdmoe_stream_t stream) {
     HDMOE_CHECK_ARG(rows && tok_rows && out && T >= 1 && K >= 1 && K <= HDMOE_MAX_EXPERTS, "combine_rows: bad args");
-    HDMOE_CHECK_ARG(D >= 4 && D % 4 == 0, "combine_rows: row width must be a multiple of 4 elements (got %lld)",
-                    (long long)D);
+    const int vecn = rows_dtype == HDMOE_BF16 ? 8 : 4;
+    HDMOE_CHECK_ARG(D >= vecn && D % vecn == 0, "combine_rows: row width must be a multiple of %d elements (got %lld)",
+                    vecn, (long long)D);
+    HDMOE_CHECK_ARG((((uintptr_t)rows | (uintptr_t)out | (uintptr_t)base) & 15) == 0, "combine_rows: 16-byte alignment");
     cudaStream_t st = (cudaStream_t)stream;
     if (rows_dtype == HDMOE_F32 && out_dtype == HDMOE_F32)
         return launch_combine<float, float>(rows, tok_rows, row_w, base, out, T, K, D, st);

@@ -103,7 +103,7 @@ int hdmoe_permute_rows(const void* const* srcs, void* const* dsts, const int64_t
  *     with r_j = tok_rows[t, j] >= 0 taken in ascending j (= ascending expert: the reference's
  *     summation order; fp32 multiply then add, no FMA contraction, so fp32 results are bit-exact).
  *     row_w == NULL means weight 1 (the backward of the permute).  `base` is the optional residual of
- *     north_star item (4); the reference passes none.
+ *     north_star item (4); the reference passes none.  D must be a multiple of 16 bytes of the row dtype.
  * ---------------------------------------------------------------------------------------------- */
 int hdmoe_combine_rows(const void* rows, int rows_dtype, const int32_t* tok_rows, const float* row_w,
                        const void* base, void* out, int out_dtype, int T, int K, int64_t D,
