@@ -9,7 +9,7 @@ NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -X
 
 all: $(LIB)
 
-build/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh) include/hdmoe_b200.h
+build/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh) $(wildcard include/*.h)
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

@@ -11,6 +11,7 @@ from . import expert_parallel  # noqa: F401
 from ._denoiser import (disable_expert_parallel, enable_expert_parallel, get_expert_dtype,  # noqa: F401
                         set_expert_dtype, set_grouped_experts)
 from .EDM_sampler import EDM_Sampler  # noqa: F401
+from .ops import set_gconv_impl  # noqa: F401
 
 __all__ = ["ops", "model_internals", "model_components", "model_config1", "model_config2", "EDM_sampler", "utils",
            "EDM_Sampler", "set_expert_dtype", "get_expert_dtype", "set_grouped_experts"]

@@ -19,9 +19,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
 // warps 2-5 = epilogue (TMEM lane quadrant = warp_id % 4).  Pipelines: smem full/empty ring (kStages),
 // TMEM full/empty (2 accumulators), static persistent tile schedule, heavy (5x5) tiles first.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc.cuh"
 #include "../../include/hdmoe_gemm.h"
 
 namespace hdmoe {
@@ -47,85 +45,6 @@ struct GConvParams {
     int32_t ksize[kMaxE];
     int32_t wrow[kMaxE];
 };
-
-// ---------------------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mb_init(uint64_t* b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(b)), "r"(count));
-}
-__device__ __forceinline__ void mb_expect_tx(uint64_t* b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mb_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(b)) : "memory");
-}
-// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
-__device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(s2u(b)), "r"(parity)
-            : "memory");
-        if (spin > (1u << 26)) {
-            printf("hdmoe gconv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
-        "[%2];" ::"r"(s2u(dst)),
-        "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-            "r"(s2u(dst)),
-        "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// K-major operand descriptor for a tile whose rows are KC*2 bytes in the matching TMA swizzle
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64))
-template <int KC>
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    constexpr uint64_t sbo = (8 * KC * 2) >> 4;                  // 8-row group pitch
-    constexpr uint64_t layout = KC == 64 ? 2 : 4;                // SWIZZLE_128B : SWIZZLE_64B
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
-        "%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 template <int KC, int N>
 struct ConvCfg {
@@ -330,22 +249,6 @@ gconv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ----------------------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)sym;
-    }
-    return fn;
-}
-
 template <int KC, int N>
 static int launch_gconv(const CUtensorMap& ta, const CUtensorMap& tb, const GConvParams& p, cudaStream_t st) {
     using Cfg = ConvCfg<KC, N>;
@@ -371,7 +274,7 @@ extern "C" int hdmoe_gconv_fwd(const void* X, const void* Wt, void* Y, int cap_r
     HDMOE_CHECK_ARG(W >= 1 && W <= 128 && 128 % W == 0 && (H * W) % 128 == 0 && H % (128 / W) == 0,
                     "gconv_fwd: need W | 128 and 128 | H*W (got %dx%d)", H, W);
     HDMOE_CHECK_ARG((((uintptr_t)X | (uintptr_t)Wt | (uintptr_t)Y) & 15) == 0, "gconv_fwd: 16-byte alignment required");
-    EncodeTiledFn enc = get_encode();
+    EncodeTiledFn enc = get_tensor_map_encoder();
     if (!enc) {
         set_error("gconv_fwd: cuTensorMapEncodeTiled not available from the driver");
         return HDMOE_ERR_CUDA;

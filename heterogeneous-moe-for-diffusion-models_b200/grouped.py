@@ -55,7 +55,7 @@ class _ConvLayer:
             rt += k * k * self.cin_rows
         self.rows_total, self.rows_total_t = r, rt
         self.w_fwd = self.w_bwd = None        # bf16 operand buffers (views)
-        self.dw = None                        # per-expert fp32 master-layout gradient accumulators (views)
+        self.dw = None                        # fp32 gradient accumulator [rows_total, cin_pad], tap-major blocks
 
 
 class _GConvFn(torch.autograd.Function):
@@ -179,18 +179,15 @@ class GroupedUnetExperts:
         n_bwd = sum(L_.rows_total_t * L_.cout for L_ in self.layers)
         self.w_fwd_all = torch.zeros(n_fwd, **bf)
         self.w_bwd_all = torch.zeros(n_bwd, **bf)
-        n_dw = sum(c.weights.numel() for L_ in self.layers for c in L_.convs)
-        self.dw_all = torch.zeros(n_dw, **f32)
+        self.dw_all = torch.zeros(n_fwd, **f32)
         o1 = o2 = o3 = 0
         for L_ in self.layers:
             L_.w_fwd = self.w_fwd_all[o1:o1 + L_.rows_total * L_.cin_pad].view(L_.rows_total, L_.cin_pad)
             o1 += L_.rows_total * L_.cin_pad
             L_.w_bwd = self.w_bwd_all[o2:o2 + L_.rows_total_t * L_.cout].view(L_.rows_total_t, L_.cout)
             o2 += L_.rows_total_t * L_.cout
-            L_.dw = []
-            for c in L_.convs:
-                L_.dw.append(self.dw_all[o3:o3 + c.weights.numel()].view_as(c.weights))
-                o3 += c.weights.numel()
+            L_.dw = self.dw_all[o3:o3 + L_.rows_total * L_.cin_pad].view(L_.rows_total, L_.cin_pad)
+            o3 += L_.rows_total * L_.cin_pad
         e0 = self.experts[0]
         tdim = e0.map_noise.weights.shape[1]
         self.lin_noise = torch.empty(E, self.emb_size, tdim, **f32)
@@ -241,7 +238,9 @@ class GroupedUnetExperts:
         for L_ in self.layers:
             for e, c in enumerate(L_.convs):
                 g = L_.gain[e] if isinstance(L_.gain, list) else L_.gain
-                ent.append(dict(w=c.weights, d_w_hat=L_.dw[e], d_w=next(it), gain=g,
+                k = L_.ks[e]
+                ent.append(dict(w=c.weights, d_w_hat=L_.dw[L_.wrow[e]:L_.wrow[e] + k * k * L_.cout], d_w=next(it), gain=g,
+                                layout="taps", cin_pad=L_.cin_pad,
                                 d_gain=gain_grads[e] if isinstance(L_.gain, list) else None))
         gain_views = [next(it) for _ in range(self.E)]
         zero = lambda t, like: t if t is not None else torch.zeros_like(like)
@@ -265,19 +264,9 @@ class GroupedUnetExperts:
 
     # ------------------------------------------------------------------------------------------ wgrad
     def weight_grad(self, layer: _ConvLayer, x, dy):
-        """dW_e += sum over the expert's rows of x (*) dy.
-        TODO(round 2): tcgen05 MN-major weight-gradient kernel (probe: tools/umma_probe.cu); until then the
-        per-expert reduction goes through the library convolution-weight-gradient on channels-last views."""
-        off = self.plan.host_offsets()
-        for e in range(self.E):
-            lo, hi = off[e], off[e + 1]
-            if hi == lo:
-                continue
-            k = layer.ks[e]
-            xin = x[lo:hi].permute(0, 3, 1, 2)[:, :layer.cin]
-            gout = dy[lo:hi].permute(0, 3, 1, 2)
-            gw = torch.nn.grad.conv2d_weight(xin, (layer.cout, layer.cin, k, k), gout, padding=(k - 1) // 2)
-            layer.dw[e].add_(gw)
+        """layer.dw (fp32, tap-major blocks) += grouped weight gradient: one tcgen05 launch for all experts."""
+        p = self.plan
+        ops.gconv_wgrad_raw(x, dy, layer.dw, p.row_expert, p.n_rows_dev, layer.ks, layer.wrow)
 
     # ------------------------------------------------------------------------------------------ forward
     def _conv(self, x, li, token, training, scale=None, act=0, residual=None, res_a=0.0, res_b=1.0):

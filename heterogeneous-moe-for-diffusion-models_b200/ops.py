@@ -487,7 +487,30 @@ def gconv_raw(x, w_cat, cout: int, w_rows_total: int, row_expert, n_rows_dev, ks
         scale = _f32c(scale)
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == y.shape
-    L.check(L.lib().hdmoe_gconv_fwd(_p(x), _p(w_cat), _p(y), cap, H, W, cin_pad, cout, w_rows_total, _p(row_expert),
-                                    _p(n_rows_dev), E, ks, wr, _p(scale), int(act), _p(residual), float(res_a),
-                                    float(res_b), _st()), "gconv_fwd")
+    fn = L.lib().hdmoe_gconv2_fwd if _GCONV_IMPL[0] == 2 else L.lib().hdmoe_gconv_fwd
+    L.check(fn(_p(x), _p(w_cat), _p(y), cap, H, W, cin_pad, cout, w_rows_total, _p(row_expert), _p(n_rows_dev), E, ks, wr,
+               _p(scale), int(act), _p(residual), float(res_a), float(res_b), _st()), "gconv_fwd")
     return y
+
+
+# 2 = halo-reuse kernel (gconv2.cu, default); 1 = per-tap loader (gconv.cu, kept for A/B measurements)
+_GCONV_IMPL = [2]
+
+
+def set_gconv_impl(v: int) -> None:
+    assert v in (1, 2)
+    _GCONV_IMPL[0] = v
+
+
+def gconv_wgrad_raw(x, dy, dw, row_expert, n_rows_dev, ksizes, wrows):
+    """dw[fp32, tap-major blocks, rows_total x cin_pad] += grouped convolution weight gradient (tcgen05)."""
+    _cuda(x, dy, dw)
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32
+    assert x.is_contiguous() and dy.is_contiguous() and dw.is_contiguous()
+    cap, H, W, cin_pad = x.shape
+    cout = dy.shape[-1]
+    E = len(ksizes)
+    ks = (C.c_int32 * E)(*ksizes)
+    wr = (C.c_int32 * E)(*wrows)
+    L.check(L.lib().hdmoe_gconv_wgrad(_p(x), _p(dy), _p(dw), cap, H, W, cin_pad, cout, dw.shape[0], _p(row_expert),
+                                      _p(n_rows_dev), E, ks, wr, _st()), "gconv_wgrad")

@@ -8,6 +8,7 @@ import hdmoe_b200
 from hdmoe_b200 import _lib as L
 
 lib = L.lib()
+FN = lib.hdmoe_gconv2_fwd if (len(sys.argv) > 1 and sys.argv[1] == 'v2') else lib.hdmoe_gconv_fwd
 dev = "cuda"
 
 
@@ -48,7 +49,7 @@ def run(R, H, W, Cin, Cout, ks, counts, scale=False, act=0, res=False, cin_real=
     scd = sc.to(dev) if scale else None
     rsd = rs.to(dev) if res else None
     p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-    rc = lib.hdmoe_gconv_fwd(p(xd), p(wd), p(y), R, H, W, Cin, Cout, tot, p(re_d), p(nr_d), E, ks_h, wr_h, p(scd), act,
+    rc = FN(p(xd), p(wd), p(y), R, H, W, Cin, Cout, tot, p(re_d), p(nr_d), E, ks_h, wr_h, p(scd), act,
                              p(rsd), 0.6, 0.8, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     L.check(rc, "gconv_fwd")
     torch.cuda.synchronize()

@@ -6,6 +6,7 @@ sys.path.insert(0, '.')
 import hdmoe_b200
 from hdmoe_b200 import _lib as L
 lib = L.lib()
+FN = lib.hdmoe_gconv2_fwd if (len(sys.argv) > 1 and sys.argv[1] == 'v2') else lib.hdmoe_gconv_fwd
 dev = "cuda"
 counts = [36, 48, 75, 97]
 ks = [3, 3, 5, 5]
@@ -30,7 +31,7 @@ for (H, Cin, Cout, mult) in [(32, 64, 32, 1), (32, 32, 32, 8), (16, 32, 32, 2), 
     wr_h = (C.c_int32 * 4)(*wrow)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     def call():
-        L.check(lib.hdmoe_gconv_fwd(p(x), p(wt), p(y), R, H, H, Cin, Cout, tot, p(re_d), p(nr_d), 4, ks_h, wr_h, None, 0,
+        L.check(FN(p(x), p(wt), p(y), R, H, H, Cin, Cout, tot, p(re_d), p(nr_d), 4, ks_h, wr_h, None, 0,
                                     None, 0.0, 0.0, st), "gconv")
     for _ in range(3):
         call()

@@ -1,0 +1,46 @@
+import ctypes as C, sys, torch, numpy as np
+lib = C.CDLL("tools/libg2trace.so")
+dev = "cuda"
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+counts, ks = [36, 48, 75, 97], [3, 3, 5, 5]
+R = sum(counts); Cin = 64; Cout = 64
+row_e = sum(([e] * c for e, c in enumerate(counts)), [])
+re_d = torch.tensor(row_e, dtype=torch.int32, device=dev); nr_d = torch.tensor([R], dtype=torch.int32, device=dev)
+p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+x = torch.randn(R, H, H, Cin, device=dev).to(torch.bfloat16)
+tot = 0; wrow = []
+for k in ks:
+    wrow.append(tot); tot += k * k * Cout
+wt = (torch.randn(tot, Cin, device=dev) / 30).to(torch.bfloat16)
+y = torch.empty(R, H, H, Cout, dtype=torch.bfloat16, device=dev)
+ks_h = (C.c_int32 * 4)(*ks); wr_h = (C.c_int32 * 4)(*wrow)
+fn = lib.hdmoe_gconv2_fwd
+fn.restype = C.c_int
+fn.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+for _ in range(3):
+    rc = fn(p(x), p(wt), p(y), R, H, H, Cin, Cout, tot, p(re_d), p(nr_d), 4, ks_h, wr_h, None, 0, None, 0.0, 0.0, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+buf = (C.c_longlong * (148 * 64))()
+lib.hdmoe_g2_trace_read.argtypes = [C.c_void_p]
+lib.hdmoe_g2_trace_read(buf)
+a = np.array(buf[:], dtype=np.int64).reshape(148, 8, 8)
+for b in (0, 1, 70, 147):
+    print("CTA", b)
+    t00 = a[b, 0, 0]
+    for t in range(8):
+        s = a[b, t, :6]
+        if s[3] == 0: break
+        print(f"  tile {t}: start +{s[0]-t00:7d}  wait_acc {s[1]-s[0]:6d}  wait_A {s[2]-s[1]:6d}  mma_issue {s[3]-s[2]:7d}  | mma_done-issue_end {s[4]-s[3]:7d}  epilogue {s[5]-s[4]:6d}")
+ends = []
+starts = []
+for b in range(148):
+    ts = [a[b, t, 5] for t in range(8) if a[b, t, 5] > 0]
+    if ts:
+        ends.append(max(ts)); starts.append(a[b, 0, 0])
+ends = np.array(ends); starts = np.array(starts)
+g0 = starts.min()
+print("first tile start spread:", (starts - g0).min(), (starts - g0).max())
+e = ends - g0
+print("CTA end times: min %d  median %d  max %d   (tiles/CTA: %s)" % (e.min(), np.median(e), e.max(),
+      np.bincount([sum(1 for t in range(8) if a[b, t, 5] > 0) for b in range(148)]).tolist()))
