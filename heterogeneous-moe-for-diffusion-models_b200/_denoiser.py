@@ -33,6 +33,14 @@ def set_grouped_experts(enabled: bool) -> None:
     _GROUPED[0] = bool(enabled)
 
 
+# ViT experts without host synchronisation (see _run_experts_on_rows); off = reference-style row slicing
+_SYNC_FREE = [True]
+
+
+def set_sync_free_vit(enabled: bool) -> None:
+    _SYNC_FREE[0] = bool(enabled)
+
+
 # expert parallelism for the U-Net MoE layer; None = every rank runs all experts (pure DP)
 _EP = {"placement": None, "group": None}
 
@@ -62,6 +70,18 @@ def _run_experts_on_rows(experts, plan, xr, tr, txr):
             runner = GroupedUnetExperts(experts)
             holder[key] = runner
         return runner(plan, xr, tr, txr, training=experts[0].training).contiguous()
+    if _SYNC_FREE[0] and all(isinstance(ex, mc.Vit_expert) for ex in experts):
+        # Sync-free (CUDA-graph-capturable) execution of the cheap ViT experts (5-13 MFLOP per sample):
+        # every expert sees all rows with static shapes and its rows are selected on the device; the reference's
+        # "only experts that received samples run" rule for the train-mode weight rewrite is kept by a device flag.
+        out = None
+        for e, expert in enumerate(experts):
+            with util.active_flag(plan.counts[e] > 0):
+                oe = expert(x=xr, time_emb=tr, text_emb=txr)
+            sel = (plan.row_expert == e).view(-1, 1, 1, 1)
+            oe = torch.where(sel, oe, torch.zeros((), dtype=oe.dtype, device=oe.device))
+            out = oe if out is None else out + oe
+        return out
     off = plan.host_offsets()
     outs = []
     for e, expert in enumerate(experts):

@@ -194,6 +194,20 @@ extern "C" int hdmoe_wprep_fwd(hdmoe_wprep_desc* descs_host, void* descs_dev, in
     return HDMOE_OK;
 }
 
+extern "C" int hdmoe_wprep_fwd_resident(const void* descs_dev, int n, int total_rows, int force, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(descs_dev && n >= 1 && total_rows >= 1, "wprep_fwd_resident: bad table");
+    wprep_fwd_kernel<<<total_rows, kWprepThreads, 0, (cudaStream_t)stream>>>((const hdmoe_wprep_desc*)descs_dev, n, force);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_wprep_bwd_multi_resident(const void* descs_dev, int n, int total_rows, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(descs_dev && n >= 1 && total_rows >= 1, "wprep_bwd_multi_resident: bad table");
+    wprep_bwd_multi_kernel<<<total_rows, kWprepThreads, 0, (cudaStream_t)stream>>>((const hdmoe_wprep_bwd_desc*)descs_dev, n);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
 extern "C" int hdmoe_wprep_bwd(const float* w, const float* d_w_hat, const float* gain_ptr, float gain, int rows,
                                int fan_in, float* d_w, float* d_gain, hdmoe_stream_t stream) {
     HDMOE_CHECK_ARG(w && d_w_hat && d_w && rows >= 1 && fan_in >= 1, "wprep_bwd: bad args");

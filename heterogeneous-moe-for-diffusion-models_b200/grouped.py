@@ -194,11 +194,18 @@ class GroupedUnetExperts:
         xdim = e0.map_text.weights.shape[1] if self.has_text else 1
         self.lin_text = torch.empty(E, self.emb_size, xdim, **f32)
         self.lin_emb = torch.empty(E, self.emb_total, self.emb_size, **f32)
+        # persistent buffers so that every launch argument is pointer-stable (CUDA-graph replay)
+        self.g_noise, self.g_text, self.g_emb = (torch.zeros_like(t) for t in (self.lin_noise, self.lin_text, self.lin_emb))
+        self.active_buf = torch.ones(E, dtype=torch.int32, device=device)
+        self.gain_grads = torch.zeros(E, **f32)
+        self.grad_flat = torch.zeros(sum(p_.numel() for p_ in self._params()), **f32)
+        self._wp = self._wpb = None
+        self._wp_sig = self._wpb_sig = None
         self._built_for = device
 
     def _entries(self):
-        """W-PREP descriptor entries (rebuilt every call: parameter storage may move)."""
-        act = [self.plan.counts[e:e + 1] for e in range(self.E)]
+        """W-PREP descriptor entries (pointer-stable: the per-expert activity flags live in a persistent buffer)."""
+        act = [self.active_buf[e:e + 1] for e in range(self.E)]
         ent = []
         for L_ in self.layers:
             for e, c in enumerate(L_.convs):
@@ -221,45 +228,69 @@ class GroupedUnetExperts:
 
     def _run_prep(self, training):
         dev = self.plan.counts.device
-        ops.WeightPrep(self._entries(), dev).run(force=training)
+        self.active_buf.copy_(self.plan.counts)
+        wp = ops.WeightPrep(self._entries(), dev) if self._wp is None else self._wp
+        sig = None
+        if self._wp is not None:
+            self._wp.entries = self._entries()
+            sig = self._wp.signature()
+        if self._wp is None or sig != self._wp_sig:
+            # (re)upload the descriptor table: first call, or parameters moved (.to(), optimizer state swap)
+            self._wp = wp
+            wp.upload()
+            self._wp_sig = wp.signature()
+        self._wp.run_uploaded(force=training)
         self.dw_all.zero_()
 
-    def _run_prep_backward(self, g_noise, g_text, g_emb):
-        dev = self.plan.counts.device
+    def _bwd_entries(self):
+        ent, o = [], 0
         params = self._params()
-        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-        views, o = [], 0
-        for p in params:
-            views.append(flat[o:o + p.numel()].view_as(p))
-            o += p.numel()
+        views = []
+        for p_ in params:
+            views.append(self.grad_flat[o:o + p_.numel()].view_as(p_))
+            o += p_.numel()
         it = iter(views)
-        ent = []
-        gain_grads = [torch.zeros((), dtype=torch.float32, device=dev) for _ in range(self.E)]
         for L_ in self.layers:
             for e, c in enumerate(L_.convs):
                 g = L_.gain[e] if isinstance(L_.gain, list) else L_.gain
                 k = L_.ks[e]
                 ent.append(dict(w=c.weights, d_w_hat=L_.dw[L_.wrow[e]:L_.wrow[e] + k * k * L_.cout], d_w=next(it), gain=g,
                                 layout="taps", cin_pad=L_.cin_pad,
-                                d_gain=gain_grads[e] if isinstance(L_.gain, list) else None))
-        gain_views = [next(it) for _ in range(self.E)]
-        zero = lambda t, like: t if t is not None else torch.zeros_like(like)
-        g_noise, g_text, g_emb = zero(g_noise, self.lin_noise), zero(g_text, self.lin_text), zero(g_emb, self.lin_emb)
-        g_noise, g_text, g_emb = g_noise.float().contiguous(), g_text.float().contiguous(), g_emb.float().contiguous()
+                                d_gain=self.gain_grads[e:e + 1] if isinstance(L_.gain, list) else None))
+        self._gain_views = [next(it) for _ in range(self.E)]
         for e, ex in enumerate(self.experts):
-            ent.append(dict(w=ex.map_noise.weights, d_w_hat=g_noise[e], d_w=next(it)))
+            ent.append(dict(w=ex.map_noise.weights, d_w_hat=self.g_noise[e], d_w=next(it)))
         if self.has_text:
             for e, ex in enumerate(self.experts):
-                ent.append(dict(w=ex.map_text.weights, d_w_hat=g_text[e], d_w=next(it)))
+                ent.append(dict(w=ex.map_text.weights, d_w_hat=self.g_text[e], d_w=next(it)))
         for kind, spec in self.program:
             if kind == "block":
                 off, co = spec["emb"]
                 for e, md in enumerate(spec["emb_mods"]):
-                    ent.append(dict(w=md.weights, d_w_hat=g_emb[e, off:off + co].contiguous(), d_w=next(it),
-                                    gain=spec["emb_gain"]))
-        ops.WeightPrepBackward(ent, dev).run()
+                    ent.append(dict(w=md.weights, d_w_hat=self.g_emb[e, off:off + co], d_w=next(it), gain=spec["emb_gain"]))
+        return ent, views
+
+    def _run_prep_backward(self, g_noise, g_text, g_emb):
+        """Accumulated operand gradients -> master-weight gradients, ONE multi-tensor launch.  The returned
+        gradients are views of a persistent buffer (call optimizer.zero_grad(set_to_none=True), the default)."""
+        dev = self.plan.counts.device
+        for buf, g in ((self.g_noise, g_noise), (self.g_text, g_text), (self.g_emb, g_emb)):
+            if g is None:
+                buf.zero_()
+            else:
+                buf.copy_(g)
+        self.gain_grads.zero_()
+        ent, views = self._bwd_entries()
+        if self._wpb is None:
+            self._wpb = ops.WeightPrepBackward(ent, dev)
+        self._wpb.entries = ent
+        sig = self._wpb.signature()
+        if sig != self._wpb_sig:
+            self._wpb.upload()
+            self._wpb_sig = sig
+        self._wpb.run_uploaded()
         for e in range(self.E):
-            gain_views[e].copy_(gain_grads[e])
+            self._gain_views[e].copy_(self.gain_grads[e])
         return views
 
     # ------------------------------------------------------------------------------------------ wgrad

@@ -12,6 +12,22 @@ import torch.nn.functional as F
 EPS = 1e-4
 _SILU_GAIN = 1.0 / 0.596
 
+# Device-side "this expert received rows" flag (0-dim bool tensor) for sync-free MoE execution: the reference
+# only runs -- and therefore only force-normalises the weights of -- experts with at least one routed sample.
+_ACTIVE = [None]
+
+
+class active_flag:
+    def __init__(self, flag):
+        self.flag = flag
+
+    def __enter__(self):
+        self.old = _ACTIVE[0]
+        _ACTIVE[0] = self.flag
+
+    def __exit__(self, *a):
+        _ACTIVE[0] = self.old
+
 
 def normalize(x: torch.Tensor, dim: Optional[Sequence[int]] = None, eps: float = EPS) -> torch.Tensor:
     """RMS-normalise: x / (eps + ||x|| * sqrt(n_norm / n_x)); ref models/model_internals.py:8-30."""
@@ -82,7 +98,8 @@ class MP_Conv(nn.Module):
         w = self.weights.to(torch.float32)
         if self.training:
             with torch.no_grad():
-                self.weights.copy_(normalize(w))
+                wn = normalize(w)
+                self.weights.copy_(wn if _ACTIVE[0] is None else torch.where(_ACTIVE[0], wn, w))
         w = normalize(w)
         w = w * (gain / math.sqrt(w[0].numel()))
         return w.to(dtype)

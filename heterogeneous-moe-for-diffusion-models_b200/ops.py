@@ -423,6 +423,32 @@ class WeightPrep:
         self._fill()      # pointers may have moved (optimizer swaps, .to())
         L.check(L.lib().hdmoe_wprep_fwd(self.descs, _p(self.dev_buf), self.n, int(bool(force)), _st()), "wprep_fwd")
 
+    def signature(self):
+        """Pointer signature of the plan: equal signatures mean the uploaded table is still valid."""
+        sig = []
+        for e in self.entries:
+            for k in ("w", "out", "out2", "active"):
+                t = e.get(k)
+                sig.append(t.data_ptr() if torch.is_tensor(t) else 0)
+            g = e.get("gain", 1.0)
+            sig.append(g.data_ptr() if torch.is_tensor(g) else float(g))
+        return tuple(sig)
+
+    def run_uploaded(self, force: bool):
+        """Launch with the table already resident on the device (no host->device copy: CUDA-graph capturable)."""
+        L.check(L.lib().hdmoe_wprep_fwd_resident(_p(self.dev_buf), self.n, self.total_rows, int(bool(force)), _st()),
+                "wprep_fwd_resident")
+
+    def upload(self):
+        self._fill()
+        tot = 0
+        for d in self.descs:
+            d.block_start = tot
+            tot += d.rows
+        self.total_rows = tot
+        host = torch.frombuffer(bytearray(bytes(self.descs)), dtype=torch.uint8)
+        self.dev_buf.copy_(host)
+
 
 class WeightPrepBackward:
     """ONE launch turning accumulated d_w_hat buffers into master-weight gradients.  entries: dicts with
@@ -435,7 +461,35 @@ class WeightPrepBackward:
         self.descs = (L.WprepBwdDesc * self.n)()
         self.dev_buf = torch.empty(self.n * C.sizeof(L.WprepBwdDesc), dtype=torch.uint8, device=device)
 
+    def upload(self):
+        self._fill()
+        tot = 0
+        for d in self.descs:
+            d.block_start = tot
+            tot += d.rows
+        self.total_rows = tot
+        host = torch.frombuffer(bytearray(bytes(self.descs)), dtype=torch.uint8)
+        self.dev_buf.copy_(host)
+
+    def run_uploaded(self):
+        L.check(L.lib().hdmoe_wprep_bwd_multi_resident(_p(self.dev_buf), self.n, self.total_rows, _st()),
+                "wprep_bwd_multi_resident")
+
+    def signature(self):
+        sig = []
+        for e in self.entries:
+            for k in ("w", "d_w_hat", "d_w", "d_gain"):
+                t = e.get(k)
+                sig.append(t.data_ptr() if torch.is_tensor(t) else 0)
+            g = e.get("gain", 1.0)
+            sig.append(g.data_ptr() if torch.is_tensor(g) else float(g))
+        return tuple(sig)
+
     def run(self):
+        self._fill()
+        L.check(L.lib().hdmoe_wprep_bwd_multi(self.descs, _p(self.dev_buf), self.n, _st()), "wprep_bwd_multi")
+
+    def _fill(self):
         for d, e in zip(self.descs, self.entries):
             w = e["w"]
             rows, fan_in = w.shape[0], w[0].numel()
@@ -453,7 +507,6 @@ class WeightPrepBackward:
             d.rows, d.fan_in, d.cin, d.taps = rows, fan_in, fan_in // taps, taps
             d.cin_pad = int(e.get("cin_pad", fan_in // taps))
             d.layout = _LAYOUTS[e.get("layout", "same")]
-        L.check(L.lib().hdmoe_wprep_bwd_multi(self.descs, _p(self.dev_buf), self.n, _st()), "wprep_bwd_multi")
 
 
 def wprep_bwd(w, d_w_hat, gain):

@@ -200,6 +200,10 @@ typedef struct {
     int32_t block_start;
 } hdmoe_wprep_bwd_desc;
 int hdmoe_wprep_bwd_multi(hdmoe_wprep_bwd_desc* descs_host, void* descs_dev, int n, hdmoe_stream_t stream);
+/* Launch-only variants for a descriptor table that is already resident on the device (block_start filled,
+ * total_rows = sum of rows): no host->device copy, so the launch can be captured into a CUDA graph. */
+int hdmoe_wprep_fwd_resident(const void* descs_dev, int n, int total_rows, int force, hdmoe_stream_t stream);
+int hdmoe_wprep_bwd_multi_resident(const void* descs_dev, int n, int total_rows, hdmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (6) Grouped implicit-GEMM convolution / GEMM on tcgen05 + TMEM + TMA -- replaces the F.conv2d /
