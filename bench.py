@@ -173,7 +173,7 @@ def run_ours(args):
     model.train()
     crit = EDM_LOSS(**LOSS)
     params = [p for p in model.parameters()]
-    opt = torch.optim.AdamW(params, lr=5e-4, fused=True)
+    opt = torch.optim.AdamW(params, lr=5e-4, fused=True, capturable=not args.no_graph)
     flat_sizes = [p.numel() for p in params]
     host = synth_batch(B, 32, rank, device, pinned=True)
     dev_batch = {k: v.to(device) for k, v in host.items()}
@@ -198,8 +198,29 @@ def run_ours(args):
         opt.step()
         return loss["loss"]
 
-    for _ in range(args.warmup):
-        step(dev_batch)
+    # whole-step CUDA graph.  The capture (and its own warm-up iterations) must be the FIRST thing that touches
+    # autograd: AccumulateGrad nodes created on the default stream by an earlier eager step would tie the legacy
+    # stream to the capturing stream.  If capture is impossible the process restarts itself in eager mode.
+    graphed, graph_note = None, "eager"
+    if not args.no_graph:
+        try:
+            from hdmoe_b200.train_step import GraphedTrainStep
+            graphed = GraphedTrainStep(step, dev_batch, warmup=max(3, args.warmup)).capture()
+            graph_note = "cuda_graph (whole step: fwd+loss+bwd+clip+AdamW" + ("+all-reduce)" if world > 1 else ")")
+        except Exception:                            # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            sys.stderr.write("bench.py: CUDA-graph capture failed, restarting in eager mode\n")
+            sys.stderr.flush()
+            os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
+    else:
+        for _ in range(args.warmup):
+            step(dev_batch)
+    barrier(world)
+    run_step = (lambda b: graphed(b)) if graphed is not None else step
+    static_in = graphed.static if graphed is not None else dev_batch
+    for _ in range(2):
+        run_step(None if graphed is not None else dev_batch)
     barrier(world)
 
     # ---- device-resident timing: K steps, CUDA events per step, L2 flushed between steps (not timed)
@@ -213,13 +234,19 @@ def run_ours(args):
             torch.cuda.synchronize()
             torch.cuda.profiler.start()      # ncu --profile-from-start off captures exactly one timed step
         s.record()
-        step(dev_batch)
+        run_step(None if graphed is not None else dev_batch)
         e.record()
         if args.profile_step and i == 0:
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
     barrier(world)
     launches = _lib.launch_count() - l0
+    if graphed is not None:
+        # graph replays do not pass through the C ABI: count the hand-written launches of ONE recorded step
+        l1 = _lib.launch_count()
+        step(dev_batch)
+        torch.cuda.synchronize()
+        launches = (_lib.launch_count() - l1) * args.steps
     ms_total = sum(s.elapsed_time(e) for s, e in ev)
     ms_total = max_over_ranks(ms_total, world, device)
     clk = clocks.stop()
@@ -234,8 +261,11 @@ def run_ours(args):
     s.record()
     loss_host = 0.0
     for _ in range(e2e_steps):
-        b = {k: v.to(device, non_blocking=True) for k, v in host.items()}
-        loss_host = float(step(b).item())        # D2H read of the step result
+        if graphed is not None:
+            loss_host = float(graphed(host).item())  # H2D into the static inputs, replay, D2H read of the loss
+        else:
+            b = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+            loss_host = float(step(b).item())        # D2H read of the step result
     e.record()
     barrier(world)
     e2e_ms = max_over_ranks(s.elapsed_time(e), world, device) / e2e_steps
@@ -255,7 +285,8 @@ def run_ours(args):
                 "config": {"workload": "model_config1 train step (fwd+EDM_LOSS+bwd+clip+AdamW), batch 256/GPU, "
                                        "4x32x32 latent, text (B,77,768), bf16 expert path, fp32 trunk (TF32 matmul)",
                            "global_batch": B * world, "parallelism": f"dp{world}",
-                           "l2": "L2 flushed (256 MiB write) between timed steps, outside the timed events"},
+                           "l2": "L2 flushed (256 MiB write) between timed steps, outside the timed events",
+                           "execution": graph_note},
                 "clocks": clk,
                 "e2e": {"value": round(e2e_value, 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3), "last_loss": loss_host},
@@ -430,6 +461,7 @@ def main():
     ap.add_argument("--profile-step", action="store_true", help="cudaProfilerStart/Stop around the first timed step")
     ap.add_argument("--full-sweep", action="store_true", help="full MoE dispatch/combine sweep (BASELINE configs[4])")
     ap.add_argument("--no-sampler", action="store_true", help="skip the EDM sampler throughput extra")
+    ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the whole-step CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
