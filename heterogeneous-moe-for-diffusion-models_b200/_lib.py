@@ -52,6 +52,8 @@ PROTOTYPES = {
     "hdmoe_gconv_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
     "hdmoe_gconv2_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
     "hdmoe_gconv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p]),
+    "hdmoe_attn_d4_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "hdmoe_attn_d4_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "hdmoe_wprep_fwd_resident": (_i, [_p, _i, _i, _i, _p]),
     "hdmoe_wprep_bwd_multi_resident": (_i, [_p, _i, _i, _p]),
     "hdmoe_wprep_bwd_multi": (_i, [_p, _p, _i, _p]),

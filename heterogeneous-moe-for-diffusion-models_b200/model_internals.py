@@ -15,6 +15,11 @@ _SILU_GAIN = 1.0 / 0.596
 # Device-side "this expert received rows" flag (0-dim bool tensor) for sync-free MoE execution: the reference
 # only runs -- and therefore only force-normalises the weights of -- experts with at least one routed sample.
 _ACTIVE = [None]
+_FUSED_ATTN = [True]     # trunk head_dim-4 attention through csrc/attention.cu (False: library SDPA, for A/B tests)
+
+
+def set_fused_attention(enabled: bool) -> None:
+    _FUSED_ATTN[0] = bool(enabled)
 
 
 class active_flag:
@@ -163,6 +168,12 @@ class MP_Attention(nn.Module):
                 k = k + self._proj(self.k_time, te, gain_t)
                 v = v + self._proj(self.v_time, te, gain_t)
         H, hd = self.num_heads, self.head_dim
+        if self.is_cross and hd == 4 and H <= 8 and q.is_cuda and q.dtype == torch.float32 and _FUSED_ATTN[0]:
+            # trunk cross-attention: fused flash-style kernel, no (B, heads, S_q, S_k) score tensor
+            from . import ops
+            o = ops.attention_d4(q, k, v, H, 1.0 / math.sqrt(hd))
+            o = self._proj(self.out_proj, o, gain_s)
+            return mp_sum(query, o, self.attn_balance)
         q = q.view(B, -1, H, hd).transpose(1, 2)
         k = k.view(B, -1, H, hd).transpose(1, 2)
         v = v.view(B, -1, H, hd).transpose(1, 2)

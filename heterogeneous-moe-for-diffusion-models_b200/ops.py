@@ -567,3 +567,41 @@ def gconv_wgrad_raw(x, dy, dw, row_expert, n_rows_dev, ksizes, wrows):
     wr = (C.c_int32 * E)(*wrows)
     L.check(L.lib().hdmoe_gconv_wgrad(_p(x), _p(dy), _p(dw), cap, H, W, cin_pad, cout, dw.shape[0], _p(row_expert),
                                       _p(n_rows_dev), E, ks, wr, _st()), "gconv_wgrad")
+
+
+# ----------------------------------------------------------------------------------------------------
+# (7) trunk attention, head_dim = 4
+# ----------------------------------------------------------------------------------------------------
+class _AttnD4(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, heads, scale):
+        _cuda(q, k, v)
+        q, k, v = _f32c(q), _f32c(k), _f32c(v)
+        B, Sq, Cc = q.shape
+        Sk = k.shape[1]
+        assert Cc == heads * 4 and k.shape == (B, Sk, Cc) and v.shape == (B, Sk, Cc)
+        o = torch.empty_like(q)
+        lse = torch.empty(B, heads, Sq, dtype=torch.float32, device=q.device)
+        L.check(L.lib().hdmoe_attn_d4_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), B, Sq, Sk, heads, float(scale), _st()),
+                "attn_d4_fwd")
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.meta = (heads, float(scale))
+        return o
+
+    @staticmethod
+    def backward(ctx, dO):
+        q, k, v, o, lse = ctx.saved_tensors
+        heads, scale = ctx.meta
+        dO = _f32c(dO)
+        B, Sq, _ = q.shape
+        Sk = k.shape[1]
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        Dbuf = torch.empty_like(lse)
+        L.check(L.lib().hdmoe_attn_d4_bwd(_p(q), _p(k), _p(v), _p(o), _p(dO), _p(lse), _p(dq), _p(dk), _p(dv), _p(Dbuf),
+                                          B, Sq, Sk, heads, scale, _st()), "attn_d4_bwd")
+        return dq, dk, dv, None, None
+
+
+def attention_d4(q, k, v, heads: int, scale: float):
+    """softmax(q k^T * scale) v per head for head_dim 4; q [B,Sq,heads*4], k/v [B,Sk,heads*4] fp32."""
+    return _AttnD4.apply(q, k, v, heads, scale)

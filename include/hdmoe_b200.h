@@ -206,6 +206,19 @@ int hdmoe_wprep_fwd_resident(const void* descs_dev, int n, int total_rows, int f
 int hdmoe_wprep_bwd_multi_resident(const void* descs_dev, int n, int total_rows, hdmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (7) Trunk attention, head_dim = 4 -- replaces the matmul / softmax / matmul chain of MP_Attention.forward,
+ *     models/model_internals.py:380-404, when there is no rel_pos_bias (cross_attn, cross_attn_text of
+ *     models/model_config2.py:279-289).  q [B,Sq,heads*4], k / v [B,Sk,heads*4], o like q, fp32, contiguous.
+ *     lse [B,heads,Sq] (log2-domain log-sum-exp of the scaled logits) is saved for the backward;
+ *     Dbuf [B,heads,Sq] is backward scratch.  heads <= 8.
+ * ---------------------------------------------------------------------------------------------- */
+int hdmoe_attn_d4_fwd(const float* q, const float* k, const float* v, float* o, float* lse, int B, int Sq, int Sk,
+                      int heads, float scale, hdmoe_stream_t stream);
+int hdmoe_attn_d4_bwd(const float* q, const float* k, const float* v, const float* o, const float* dO,
+                      const float* lse, float* dq, float* dk, float* dv, float* Dbuf, int B, int Sq, int Sk,
+                      int heads, float scale, hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (6) Grouped implicit-GEMM convolution / GEMM on tcgen05 + TMEM + TMA -- replaces the F.conv2d /
  *     F.linear calls of MP_Conv inside the experts (models/model_internals.py:261-271), for ALL
  *     experts of one layer in a single persistent launch.  Declared in hdmoe_gemm.h.

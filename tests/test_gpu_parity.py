@@ -548,3 +548,24 @@ def test_grouped_tcgen05_unet_experts_match_per_expert_path(train):
         assert rel_l2(torch.cat(a_all), torch.cat(b_all)) < 5e-2
         for n, w in res["loop"]["w"].items():                        # forced weight norm applied identically (Q6)
             assert rel_l2(res["grouped"]["w"][n], w) < 1e-5, n
+
+
+# ------------------------------------------------------------------------------------------------ trunk attention
+@pytest.mark.parametrize("B,Sq,Sk,H", [(2, 1024, 1024, 8), (3, 1024, 77, 8), (2, 100, 37, 2), (1, 4096, 4096, 8)])
+def test_attention_d4_matches_reference_math(B, Sq, Sk, H):
+    """softmax(QK^T/sqrt(d))V for d = 4 (models/model_internals.py:380-404, no rel_pos_bias) fwd + bwd."""
+    from hdmoe_b200 import ops
+    gen = torch.Generator().manual_seed(B + Sq + Sk)
+    q, k, v = (torch.randn(B, s, H * 4, generator=gen) for s in (Sq, Sk, Sk))
+    gy = torch.randn(B, Sq, H * 4, generator=gen)
+    ref_in = [t.double().requires_grad_(True) for t in (q, k, v)]
+    qh, kh, vh = (t.view(B, -1, H, 4).transpose(1, 2) for t in ref_in)
+    p = (torch.matmul(qh, kh.transpose(-2, -1)) / 2.0).softmax(dim=-1)
+    ref = torch.matmul(p, vh).transpose(1, 2).reshape(B, Sq, H * 4)
+    (ref * gy.double()).sum().backward()
+    d_in = [t.cuda().requires_grad_(True) for t in (q, k, v)]
+    out = ops.attention_d4(d_in[0], d_in[1], d_in[2], H, 0.5)
+    (out * gy.cuda()).sum().backward()
+    assert rel_l2(out.cpu(), ref) < TOL32
+    for a, b, n in zip(d_in, ref_in, "qkv"):
+        assert rel_l2(a.grad.cpu(), b.grad) < 2e-5, n
