@@ -169,6 +169,11 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = True
     hdmoe_b200.set_expert_dtype(torch.bfloat16)
     B = args.batch
+    if args.parallelism == "ep" and world > 1:
+        # U-Net experts sharded over the ranks (cost-balanced), NCCL all-to-all dispatch / combine; the split sizes
+        # are read on the host, so this mode runs the eager step (no whole-step graph)
+        hdmoe_b200.enable_expert_parallel([3, 3, 5, 5])
+        args.no_graph = True
     model = build_model(1, device)
     model.train()
     crit = EDM_LOSS(**LOSS)
@@ -284,7 +289,9 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": "model_config1 train step (fwd+EDM_LOSS+bwd+clip+AdamW), batch 256/GPU, "
                                        "4x32x32 latent, text (B,77,768), bf16 expert path, fp32 trunk (TF32 matmul)",
-                           "global_batch": B * world, "parallelism": f"dp{world}",
+                           "global_batch": B * world,
+                           "parallelism": (f"ep{world} (U-Net experts) + dp{world} (trunk)" if args.parallelism == "ep" and world > 1
+                                           else f"dp{world}"),
                            "l2": "L2 flushed (256 MiB write) between timed steps, outside the timed events",
                            "execution": graph_note},
                 "clocks": clk,
@@ -380,8 +387,8 @@ def sampler_throughput(device, B=1024, steps=18):
     gen = torch.Generator().manual_seed(SEED)
     noise = torch.randn(B, 4, 32, 32, generator=gen).to(device)
     text = torch.randn(B, 77, 768, generator=gen).to(device)
-    smp = hdmoe_b200.EDM_Sampler(model, model, num_solve_steps=steps, guidance=1.0)
-    smp.sample(noise[:64], text[:64], P_MEAN, P_STD)     # warm-up (allocator, autotune)
+    smp = hdmoe_b200.EDM_Sampler(model, model, num_solve_steps=steps, guidance=1.0, use_cuda_graph=True)
+    smp.sample(noise, text, P_MEAN, P_STD)               # warm-up: allocator, autotune, graph capture
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     smp.nfe = 0
@@ -391,7 +398,8 @@ def sampler_throughput(device, B=1024, steps=18):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
     return {"metric": "EDM sample img/s", "value": round(B / (ms / 1e3), 1), "unit": "img/s", "batch": B, "nfe": smp.nfe,
-            "ms": round(ms, 1), "finite": bool(torch.isfinite(out).all())}
+            "ms": round(ms, 1), "finite": bool(torch.isfinite(out).all()),
+            "execution": "one CUDA graph per denoiser evaluation, fused Heun kernels between"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -461,6 +469,7 @@ def main():
     ap.add_argument("--profile-step", action="store_true", help="cudaProfilerStart/Stop around the first timed step")
     ap.add_argument("--full-sweep", action="store_true", help="full MoE dispatch/combine sweep (BASELINE configs[4])")
     ap.add_argument("--no-sampler", action="store_true", help="skip the EDM sampler throughput extra")
+    ap.add_argument("--parallelism", default="dp", choices=["dp", "ep"], help="N>1: data-parallel replicas or expert-parallel U-Net experts")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the whole-step CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -1,0 +1,75 @@
+"""Multi-GPU (NCCL) parity of the expert-parallel MoE layer: needs >= 2 GPUs (`gpurun --gpus 2`)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import FULL, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import hdmoe_b200
+        from hdmoe_b200 import model_config2
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        torch.manual_seed(0)
+        model = model_config2.preconditioned_HDMOEM(**FULL)
+        gen = torch.Generator().manual_seed(100)
+        with torch.no_grad():
+            for p in model.parameters():
+                if float(p.abs().max()) == 0:
+                    p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
+        model.cuda().eval()
+        B = 8
+        gen = torch.Generator().manual_seed(1234 + rank)          # every rank has its own samples
+        x0 = torch.randn(B, 4, 32, 32, generator=gen) * 0.5
+        sigma = torch.exp(torch.randn(B, 1, 1, 1, generator=gen) * 1.6 - 1.2).clamp(0.002, 80.0)
+        x = (x0 + sigma * torch.randn(x0.shape, generator=gen)).cuda().requires_grad_(True)
+        text = torch.randn(B, 77, 768, generator=gen).cuda()
+        ones = torch.ones(B, 4).cuda()
+        res = {}
+        for dt in (torch.float32, torch.bfloat16):
+            hdmoe_b200.set_expert_dtype(dt)
+            outs = {}
+            for mode in ("local", "ep"):
+                if mode == "ep":
+                    hdmoe_b200.enable_expert_parallel([3, 3, 5, 5])
+                else:
+                    hdmoe_b200.disable_expert_parallel()
+                x.grad = None
+                out = model(x=x, sigma=sigma.cuda(), text_emb=text, Unet_router_mask=ones, Vit_router_mask=ones, zeta=0,
+                            transition_point=-1.2, softness=1.6)["denoised"]
+                out.square().mean().backward()
+                outs[mode] = (out.detach().float().cpu(), x.grad.detach().cpu().clone())
+            res[str(dt)] = (rel_l2(outs["ep"][0], outs["local"][0]), rel_l2(outs["ep"][1], outs["local"][1]))
+        hdmoe_b200.disable_expert_parallel()
+        hdmoe_b200.set_expert_dtype(torch.float32)
+        ret[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_expert_parallel_matches_local_experts_nccl():
+    world, port = 2, _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    for rank in range(world):
+        r = ret[rank]
+        assert r["torch.float32"][0] < 1e-5 and r["torch.float32"][1] < 1e-4, r      # same kernels, rows only moved
+        assert r["torch.bfloat16"][0] < 2e-2 and r["torch.bfloat16"][1] < 5e-2, r

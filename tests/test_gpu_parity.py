@@ -569,3 +569,16 @@ def test_attention_d4_matches_reference_math(B, Sq, Sk, H):
     assert rel_l2(out.cpu(), ref) < TOL32
     for a, b, n in zip(d_in, ref_in, "qkv"):
         assert rel_l2(a.grad.cpu(), b.grad) < 2e-5, n
+
+
+def test_sampler_cuda_graph_matches_eager():
+    """Graph-replayed denoiser evaluations give the same latents as the eager loop (same kernels, same order)."""
+    from hdmoe_b200 import EDM_Sampler
+    g = load_golden("sampler_cfg2_g1")
+    model = _load_model(2, dict(TINY, top_k=1), golden_weights(g), False)
+    noise, text = g["in.noise"].cuda(), g["in.text"].cuda()
+    a = EDM_Sampler(model, model, num_solve_steps=5).sample(noise, text, -1.2, 1.6)
+    smp = EDM_Sampler(model, model, num_solve_steps=5, use_cuda_graph=True)
+    b = smp.sample(noise, text, -1.2, 1.6)
+    assert smp.nfe == 9
+    assert rel_l2(b.cpu(), a.cpu()) < 1e-5
