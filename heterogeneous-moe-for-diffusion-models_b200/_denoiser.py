@@ -33,6 +33,14 @@ def set_grouped_experts(enabled: bool) -> None:
     _GROUPED[0] = bool(enabled)
 
 
+# one multi-tensor W-PREP launch for all trunk / router MP_Conv weights (prepared.py)
+_TRUNK_PREP = [True]
+
+
+def set_trunk_weight_prep(enabled: bool) -> None:
+    _TRUNK_PREP[0] = bool(enabled)
+
+
 # ViT experts without host synchronisation (see _run_experts_on_rows); off = reference-style row slicing
 _SYNC_FREE = [True]
 
@@ -74,13 +82,20 @@ def _run_experts_on_rows(experts, plan, xr, tr, txr):
         # Sync-free (CUDA-graph-capturable) execution of the cheap ViT experts (5-13 MFLOP per sample):
         # every expert sees all rows with static shapes and its rows are selected on the device; the reference's
         # "only experts that received samples run" rule for the train-mode weight rewrite is kept by a device flag.
+        from . import prepared
+        holder = experts.__dict__ if isinstance(experts, nn.ModuleList) else experts[0].__dict__
+        grp = holder.get("_hdmoe_prepared")
+        if grp is None or grp.out_dtype != xr.dtype:
+            grp = prepared.vit_expert_group(experts, xr.dtype)
+            holder["_hdmoe_prepared"] = grp
         out = None
-        for e, expert in enumerate(experts):
-            with util.active_flag(plan.counts[e] > 0):
-                oe = expert(x=xr, time_emb=tr, text_emb=txr)
-            sel = (plan.row_expert == e).view(-1, 1, 1, 1)
-            oe = torch.where(sel, oe, torch.zeros((), dtype=oe.dtype, device=oe.device))
-            out = oe if out is None else out + oe
+        with grp.prepared(experts[0].training, plan.counts):
+            for e, expert in enumerate(experts):
+                with util.active_flag(plan.counts[e] > 0):
+                    oe = expert(x=xr, time_emb=tr, text_emb=txr)
+                sel = (plan.row_expert == e).view(-1, 1, 1, 1)
+                oe = torch.where(sel, oe, torch.zeros((), dtype=oe.dtype, device=oe.device))
+                out = oe if out is None else out + oe
         return out
     off = plan.host_offsets()
     outs = []
@@ -186,6 +201,20 @@ class HDMOEM(nn.Module):
     def _forward(self, x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point=None,
                  softness=None, alpha_routing: float = 10, noise: Optional[dict] = None):
         noise = noise or {}
+        if x.is_cuda and _TRUNK_PREP[0]:
+            from . import prepared
+            grp = self.__dict__.get("_hdmoe_trunk_group")
+            if grp is None:
+                grp = prepared.trunk_group(self)
+                self.__dict__["_hdmoe_trunk_group"] = grp
+            with grp.prepared(self.training):
+                return self._forward_body(x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point,
+                                          softness, alpha_routing, noise)
+        return self._forward_body(x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point,
+                                  softness, alpha_routing, noise)
+
+    def _forward_body(self, x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point, softness,
+                      alpha_routing, noise):
         B, _, H, W = x.shape
         te = self.out_fourier1(self.Fourier_emb(time_vec))
         te = self.out_fourier2(util.mp_silu(te))

@@ -100,6 +100,10 @@ class MP_Conv(nn.Module):
         self.stride = stride
 
     def prepared_weight(self, gain=1.0, dtype=torch.float32) -> torch.Tensor:
+        from . import prepared
+        pw = prepared.lookup(self, gain)      # jointly prepared by a PreparedGroup (one launch for many layers)
+        if pw is not None:
+            return pw if pw.dtype == dtype else pw.to(dtype)
         w = self.weights.to(torch.float32)
         if self.training:
             with torch.no_grad():
