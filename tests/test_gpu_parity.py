@@ -576,9 +576,24 @@ def test_sampler_cuda_graph_matches_eager():
     from hdmoe_b200 import EDM_Sampler
     g = load_golden("sampler_cfg2_g1")
     model = _load_model(2, dict(TINY, top_k=1), golden_weights(g), False)
-    noise, text = g["in.noise"].cuda(), g["in.text"].cuda()
-    a = EDM_Sampler(model, model, num_solve_steps=5).sample(noise, text, -1.2, 1.6)
-    smp = EDM_Sampler(model, model, num_solve_steps=5, use_cuda_graph=True)
-    b = smp.sample(noise, text, -1.2, 1.6)
+    import hdmoe_b200
+    from hdmoe_b200 import model_config2
+    # graph replay needs the sync-free expert path: bf16 grouped U-Net experts at the shipped hyper-parameters
+    torch.manual_seed(0)
+    model = model_config2.preconditioned_HDMOEM(**FULL).cuda().eval()
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for p_ in model.parameters():
+            if float(p_.abs().max()) == 0:
+                p_.copy_((torch.randn(p_.shape, generator=gen) * 0.3).cuda())
+    noise = torch.randn(4, 4, 32, 32, generator=gen).cuda()
+    text = torch.randn(4, 77, 768, generator=gen).cuda()
+    hdmoe_b200.set_expert_dtype(torch.bfloat16)
+    try:
+        a = EDM_Sampler(model, model, num_solve_steps=5).sample(noise, text, -1.2, 1.6)
+        smp = EDM_Sampler(model, model, num_solve_steps=5, use_cuda_graph=True)
+        b = smp.sample(noise, text, -1.2, 1.6)
+    finally:
+        hdmoe_b200.set_expert_dtype(torch.float32)
     assert smp.nfe == 9
     assert rel_l2(b.cpu(), a.cpu()) < 1e-5
