@@ -178,19 +178,22 @@ def run_ours(args):
     model.train()
     crit = EDM_LOSS(**LOSS)
     params = [p for p in model.parameters()]
-    opt = torch.optim.AdamW(params, lr=5e-4, fused=True, capturable=not args.no_graph)
+    opt = torch.optim.AdamW(params, lr=5e-4, fused=True, capturable=(not args.no_graph) and world == 1)
     flat_sizes = [p.numel() for p in params]
     host = synth_batch(B, 32, rank, device, pinned=True)
     dev_batch = {k: v.to(device) for k, v in host.items()}
     zeta = 2.0
     flush = L2Flusher(device)
 
-    def step(b):
+    def fwd_bwd(b):
         out = model(x=b["x"], sigma=b["sigma"], text_emb=b["text"], Unet_router_mask=b["um"],
                     Vit_router_mask=b["vm"], zeta=zeta, return_log_var=True)
         loss = crit(b["sigma"], b["x0"], b["sigma"], out)
         opt.zero_grad(set_to_none=True)
         loss["loss"].backward()
+        return loss["loss"]
+
+    def reduce_and_update():
         if world > 1:
             import torch.distributed as dist
             grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
@@ -201,7 +204,11 @@ def run_ours(args):
                 p.grad = g.view_as(p)
         torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
-        return loss["loss"]
+
+    def step(b):
+        loss = fwd_bwd(b)
+        reduce_and_update()
+        return loss
 
     # whole-step CUDA graph.  The capture (and its own warm-up iterations) must be the FIRST thing that touches
     # autograd: AccumulateGrad nodes created on the default stream by an earlier eager step would tie the legacy
@@ -210,11 +217,29 @@ def run_ours(args):
     if not args.no_graph:
         try:
             from hdmoe_b200.train_step import GraphedTrainStep
-            graphed = GraphedTrainStep(step, dev_batch, warmup=max(3, args.warmup)).capture()
-            graph_note = "cuda_graph (whole step: fwd+loss+bwd+clip+AdamW" + ("+all-reduce)" if world > 1 else ")")
+            if world == 1:
+                graphed = GraphedTrainStep(step, dev_batch, warmup=max(3, args.warmup)).capture()
+                graph_note = "cuda_graph (whole step: fwd+loss+bwd+clip+AdamW)"
+            else:
+                # N > 1: the graph holds forward+loss+backward; the NCCL gradient all-reduce, clipping and AdamW run
+                # eagerly after each replay (keeps the collective out of stream capture)
+                inner = GraphedTrainStep(fwd_bwd, dev_batch, warmup=max(3, args.warmup)).capture()
+
+                class _Outer:
+                    static = inner.static
+
+                    def __call__(self, batch=None):
+                        loss = inner(batch)
+                        reduce_and_update()
+                        return loss
+
+                graphed = _Outer()
+                graph_note = "cuda_graph (fwd+loss+bwd) + eager all-reduce/clip/AdamW"
         except Exception:                            # noqa: BLE001
             import traceback
             traceback.print_exc()
+            if world > 1:
+                raise
             sys.stderr.write("bench.py: CUDA-graph capture failed, restarting in eager mode\n")
             sys.stderr.flush()
             os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
