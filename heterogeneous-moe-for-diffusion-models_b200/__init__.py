@@ -9,9 +9,9 @@ from . import _lib, ops  # noqa: F401
 from . import model_internals, model_components, model_config1, model_config2, EDM_sampler, utils  # noqa: F401
 from . import expert_parallel  # noqa: F401
 from ._denoiser import (disable_expert_parallel, enable_expert_parallel, get_expert_dtype,  # noqa: F401
-                        set_expert_dtype, set_grouped_experts)
+                        set_expert_dtype, set_grouped_experts, set_branch_streams)
 from .EDM_sampler import EDM_Sampler  # noqa: F401
 from .ops import set_gconv_impl  # noqa: F401
 
 __all__ = ["ops", "model_internals", "model_components", "model_config1", "model_config2", "EDM_sampler", "utils",
-           "EDM_Sampler", "set_expert_dtype", "get_expert_dtype", "set_grouped_experts"]
+           "EDM_Sampler", "set_expert_dtype", "get_expert_dtype", "set_grouped_experts", "set_branch_streams"]

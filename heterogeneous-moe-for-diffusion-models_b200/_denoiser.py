@@ -49,6 +49,53 @@ def set_sync_free_vit(enabled: bool) -> None:
     _SYNC_FREE[0] = bool(enabled)
 
 
+# Independent branches on separate CUDA streams: the four ViT experts (tiny launch-latency-bound kernels, 5-13
+# MFLOP per sample) and the whole ViT router + MoE branch run beside the U-Net branch.  Inside a captured step the
+# fork/join becomes parallel graph branches; backward follows automatically (autograd replays every node on the
+# stream of its forward).  Program order on the host is unchanged, so RNG consumption order (quirk Q2) is kept.
+_BRANCH_STREAMS = [True]
+_side_streams = {}
+
+
+def set_branch_streams(enabled: bool) -> None:
+    _BRANCH_STREAMS[0] = bool(enabled)
+
+
+def _streams(device, tag: str, n: int):
+    key = (device, tag)
+    lst = _side_streams.setdefault(key, [])
+    while len(lst) < n:
+        lst.append(torch.cuda.Stream(device=device))
+    return lst[:n]
+
+
+class _fork:
+    """with _fork(stream, inputs): ... runs the body on `stream` after everything queued on the current stream."""
+
+    def __init__(self, stream, inputs=()):
+        self.s, self.inputs = stream, inputs
+
+    def __enter__(self):
+        self.main = torch.cuda.current_stream()
+        self.s.wait_stream(self.main)
+        for t in self.inputs:
+            if t is not None:
+                t.record_stream(self.s)
+        self.ctx = torch.cuda.stream(self.s)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self.ctx.__exit__(*exc)
+
+    def join(self, *outputs):
+        main = torch.cuda.current_stream()
+        main.wait_stream(self.s)
+        for t in outputs:
+            if t is not None:
+                t.record_stream(main)
+
+
 # expert parallelism for the U-Net MoE layer (SURVEY §8e); None = every rank runs all experts (pure DP)
 _EP = {"placement": None, "group": None}
 
@@ -88,14 +135,27 @@ def _run_experts_on_rows(experts, plan, xr, tr, txr):
         if grp is None or grp.out_dtype != xr.dtype:
             grp = prepared.vit_expert_group(experts, xr.dtype)
             holder["_hdmoe_prepared"] = grp
-        out = None
+        def one(e, expert):
+            with util.active_flag(plan.counts[e] > 0):
+                oe = expert(x=xr, time_emb=tr, text_emb=txr)
+            sel = (plan.row_expert == e).view(-1, 1, 1, 1)
+            return torch.where(sel, oe, torch.zeros((), dtype=oe.dtype, device=oe.device))
+
+        outs = []
         with grp.prepared(experts[0].training, plan.counts):
-            for e, expert in enumerate(experts):
-                with util.active_flag(plan.counts[e] > 0):
-                    oe = expert(x=xr, time_emb=tr, text_emb=txr)
-                sel = (plan.row_expert == e).view(-1, 1, 1, 1)
-                oe = torch.where(sel, oe, torch.zeros((), dtype=oe.dtype, device=oe.device))
-                out = oe if out is None else out + oe
+            if _BRANCH_STREAMS[0] and xr.is_cuda:
+                forks = []
+                for e, (expert, st) in enumerate(zip(experts, _streams(xr.device, "vit", len(experts)))):
+                    with _fork(st, (xr, tr, txr, plan.counts, plan.row_expert)) as fk:
+                        outs.append(one(e, expert))
+                    forks.append(fk)
+                for fk, oe in zip(forks, outs):
+                    fk.join(oe)
+            else:
+                outs = [one(e, expert) for e, expert in enumerate(experts)]
+        out = outs[0]
+        for oe in outs[1:]:
+            out = out + oe
         return out
     off = plan.host_offsets()
     outs = []
@@ -231,12 +291,24 @@ class HDMOEM(nn.Module):
         in_unet = s_unet * feats
         in_vit = s_vit * feats
         # the ViT router is evaluated first (RNG order, quirk Q2)
-        w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
-                                                noise=noise.get("vit"))
-        w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
-                                              noise=noise.get("unet"))
-        out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k)
-        out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k)
+        if _BRANCH_STREAMS[0] and x.is_cuda and _EP["placement"] is None:
+            # ViT branch (router + MoE layer) beside the U-Net branch; host program order as in the reference
+            with _fork(_streams(x.device, "branch", 1)[0], (in_vit, te, text_emb, Vit_router_mask)) as fk:
+                w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
+                                                        noise=noise.get("vit"))
+            w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
+                                                  noise=noise.get("unet"))
+            out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k)
+            with torch.cuda.stream(fk.s):
+                out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k)
+            fk.join(w_vit, p_vit, raw_vit, out_v)
+        else:
+            w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
+                                                    noise=noise.get("vit"))
+            w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
+                                                  noise=noise.get("unet"))
+            out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k)
+            out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k)
         uf = out_u.flatten(2).transpose(1, 2)
         vf = out_v.flatten(2).transpose(1, 2)
         if self._variant == 2:

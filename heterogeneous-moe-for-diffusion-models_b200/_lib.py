@@ -52,6 +52,16 @@ PROTOTYPES = {
     "hdmoe_gconv_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
     "hdmoe_gconv2_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
     "hdmoe_gconv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p]),
+    "hdmoe_nhwc_pixnorm_silu_fwd": (_i, [_p, _p, _p, _i64, _i, _p]),
+    "hdmoe_nhwc_pixnorm_silu_bwd": (_i, [_p, _p, _p, _p, _i64, _i, _p]),
+    "hdmoe_nhwc_gain_silu_fwd": (_i, [_p, _p, _p, _i64, _i64, _i, _p]),
+    "hdmoe_nhwc_gain_silu_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _p]),
+    "hdmoe_nhwc_axpby": (_i, [_p, _p, _f, _f, _p, _i64, _p]),
+    "hdmoe_nhwc_scale2": (_i, [_p, _f, _f, _p, _p, _i64, _p]),
+    "hdmoe_nhwc_cat": (_i, [_p, _p, _f, _f, _i, _i, _p, _i64, _p]),
+    "hdmoe_nhwc_split": (_i, [_p, _f, _f, _i, _i, _p, _p, _i64, _p]),
+    "hdmoe_nchw_to_nhwc": (_i, [_p, _p, _i64, _i, _i, _i64, _i, _p]),
+    "hdmoe_nhwc_to_nchw": (_i, [_p, _p, _i64, _i, _i, _i64, _p]),
     "hdmoe_attn_d4_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "hdmoe_attn_d4_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "hdmoe_wprep_fwd_resident": (_i, [_p, _i, _i, _i, _p]),

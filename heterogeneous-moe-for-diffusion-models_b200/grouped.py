@@ -25,6 +25,7 @@ import torch.nn.functional as F
 
 from . import model_components as mc
 from . import model_internals as m
+from . import nhwc
 from . import ops
 
 EPS = 1e-4
@@ -310,11 +311,6 @@ class GroupedUnetExperts:
                              layer.wrow, scale=scale, act=act, residual=residual, res_a=res_a, res_b=res_b)
 
     @staticmethod
-    def _pixel_norm(x):
-        n = torch.linalg.vector_norm(x, dim=-1, keepdim=True, dtype=torch.float32)
-        return x / (EPS + n * (1.0 / math.sqrt(x.shape[-1]))).to(x.dtype)
-
-    @staticmethod
     def _resample(x, mode):
         if mode == "keep":
             return x
@@ -349,11 +345,7 @@ class GroupedUnetExperts:
         emb = m.mp_silu(emb)
         gains = 1 + self._select(torch.einsum("rk,eok->reo", emb, We), idx)        # [cap, sum Cout_b] fp32
         # input: NHWC, ones channel appended (models/model_components.py:416), zero-padded to the K chunk
-        R, C, H, W = x_rows.shape
-        cin_pad0 = self.layers[0].cin_pad
-        x = torch.zeros(R, H, W, cin_pad0, dtype=torch.bfloat16, device=dev)
-        x[..., :C] = x_rows.permute(0, 2, 3, 1)
-        x[..., C] = 1.0
+        x = nhwc.rows_to_nhwc(x_rows.to(torch.bfloat16).contiguous(), self.layers[0].cin_pad)
         use = need_grad
         skips = []
         for kind, item in self.program:
@@ -363,31 +355,34 @@ class GroupedUnetExperts:
                 continue
             s = item
             if s["cat"]:
-                x = m.mp_cat(x, skips.pop(), dim=3, t=e0.concat_balance)
+                x = nhwc.mp_cat(x.contiguous(), skips.pop().contiguous(), e0.concat_balance)
             x = self._resample(x, s["resample"])
             off, co = s["emb"]
             g = gains[:, off:off + co]
             t = s["t"]
             c = math.sqrt((1 - t) ** 2 + t ** 2)
+            x = x.contiguous()
             if s["type"] == "enc":
                 if s["skip"] is not None:
                     x = self._conv(x, s["skip"], token, use)
-                x = self._pixel_norm(x)
+                x, a = nhwc.pixnorm_silu(x)
+            else:
+                a = nhwc.gain_silu(x)
             if use:
-                y = self._conv(m.mp_silu(x), s["res1"], token, True)
-                y = m.mp_silu(y * g[:, None, None, :].to(y.dtype))
+                y = self._conv(a, s["res1"], token, True)
+                y = nhwc.gain_silu(y, g)
                 if s["dropout"]:
                     y = F.dropout(y, p=s["dropout"])
                 y = self._conv(y, s["res2"], token, True)
                 if s["type"] == "dec" and s["skip"] is not None:
                     x = self._conv(x, s["skip"], token, True)
-                x = m.mp_sum(x, y, t=t)
+                x = nhwc.mp_sum(x, y, t)
             else:   # fused epilogues: mp_silu(conv * (1+emb)) and mp_sum(x, conv, t)
-                y = self._conv(m.mp_silu(x), s["res1"], token, False, scale=g, act=1)
+                y = self._conv(a, s["res1"], token, False, scale=g, act=1)
                 if s["type"] == "dec" and s["skip"] is not None:
                     x = self._conv(x, s["skip"], token, False)
                 x = self._conv(y, s["res2"], token, False, residual=x.contiguous(), res_a=(1 - t) / c, res_b=t / c)
             if "encoders" in s["name"]:
                 skips.append(x)
         x = self._conv(x, self.out_li, token, use)
-        return x.permute(0, 3, 1, 2)
+        return nhwc.nhwc_to_rows(x)

@@ -11,6 +11,13 @@ from . import model_internals as m
 from . import ops
 
 
+_CHANNELS_LAST = [False]   # measured: no gain on B200 (cuDNN picks NHWC kernels either way)
+
+
+def set_router_channels_last(enabled: bool) -> None:
+    _CHANNELS_LAST[0] = bool(enabled)
+
+
 class Scaling_router(nn.Module):
     """Soft 2-way gain router of model_config1 (ref models/model_components.py:7-66)."""
 
@@ -72,6 +79,9 @@ class Router(nn.Module):
     def forward(self, x: torch.Tensor, time_emb: torch.Tensor, mask: Optional[torch.Tensor] = None,
                 zeta: Optional[float] = 1e-2, noise: Optional[torch.Tensor] = None):
         B = x.shape[0]
+        if x.is_cuda and _CHANNELS_LAST[0]:
+            # NHWC trunk: the library convolutions run channels-last natively (no NCHW<->NHWC conversion kernels)
+            x = x.contiguous(memory_format=torch.channels_last)
         pooled = self.hard_route(x).reshape(B, -1).float()
         if time_emb.ndim == 3:
             time_emb = time_emb.squeeze(1)

@@ -119,6 +119,8 @@ class MP_Conv(nn.Module):
             return F.linear(x, w)
         assert x.ndim == 4
         k = w.shape[-1]
+        if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+            w = w.contiguous(memory_format=torch.channels_last)
         if self.stride != 1:
             return F.conv2d(x, w, padding=k // 2, stride=self.stride)
         lo = (k - 1) // 2

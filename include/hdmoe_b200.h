@@ -219,6 +219,33 @@ int hdmoe_attn_d4_bwd(const float* q, const float* k, const float* v, const floa
                       int heads, float scale, hdmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (8) Fused NHWC bf16 elementwise kernels of the U-Net expert block -- replace the elementwise ATen chains of
+ *     Unet_block.forward (models/model_components.py:232-253) and of Unet_expert.forward (:416, :428):
+ *       pixnorm_silu : xn = x / (1e-4 + ||x||_C / sqrt(C)),  a = mp_silu(xn)            (:238, :240)
+ *       gain_silu    : y = mp_silu(z * gain[row, c])   (gain NULL -> plain mp_silu)      (:242-243)
+ *       axpby/scale2 : mp_sum(x, y, t) = ca*x + cb*y and its backward                    (:253)
+ *       cat/split    : mp_cat along channels and its backward                            (:428)
+ *       nchw_to_nhwc / nhwc_to_nchw : layout change at the dispatch / combine boundary (+ ones channel, :416)
+ *     All tensors bf16, channel counts multiples of 8, 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+int hdmoe_nhwc_pixnorm_silu_fwd(const void* x, void* xn, void* a, int64_t npix, int C, hdmoe_stream_t stream);
+int hdmoe_nhwc_pixnorm_silu_bwd(const void* x, const void* g_xn, const void* g_a, void* dx, int64_t npix, int C,
+                                hdmoe_stream_t stream);
+int hdmoe_nhwc_gain_silu_fwd(const void* z, const float* gain, void* y, int64_t rows, int64_t pix_per_row, int C,
+                             hdmoe_stream_t stream);
+int hdmoe_nhwc_gain_silu_bwd(const void* z, const float* gain, const void* dy, void* dz, float* dgain, int64_t rows,
+                             int64_t pix_per_row, int C, hdmoe_stream_t stream);
+int hdmoe_nhwc_axpby(const void* x, const void* y, float ca, float cb, void* out, int64_t n, hdmoe_stream_t stream);
+int hdmoe_nhwc_scale2(const void* g, float ca, float cb, void* gx, void* gy, int64_t n, hdmoe_stream_t stream);
+int hdmoe_nhwc_cat(const void* a, const void* b, float wa, float wb, int Ca, int Cb, void* out, int64_t npix,
+                   hdmoe_stream_t stream);
+int hdmoe_nhwc_split(const void* g, float wa, float wb, int Ca, int Cb, void* ga, void* gb, int64_t npix,
+                     hdmoe_stream_t stream);
+int hdmoe_nchw_to_nhwc(const void* src, void* dst, int64_t rows, int Cs, int Cd, int64_t HW, int one_channel,
+                       hdmoe_stream_t stream);
+int hdmoe_nhwc_to_nchw(const void* src, void* dst, int64_t rows, int Cs, int Cd, int64_t HW, hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (6) Grouped implicit-GEMM convolution / GEMM on tcgen05 + TMEM + TMA -- replaces the F.conv2d /
  *     F.linear calls of MP_Conv inside the experts (models/model_internals.py:261-271), for ALL
  *     experts of one layer in a single persistent launch.  Declared in hdmoe_gemm.h.

@@ -597,3 +597,84 @@ def test_sampler_cuda_graph_matches_eager():
         hdmoe_b200.set_expert_dtype(torch.float32)
     assert smp.nfe == 9
     assert rel_l2(b.cpu(), a.cpu()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused NHWC elementwise kernels (csrc/nhwc_ops.cu) vs the fp32 torch restatement of the same expressions
+# ------------------------------------------------------------------------------------------------------------
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C", [32, 64, 128])
+def test_nhwc_pixnorm_silu(C):
+    from hdmoe_b200 import nhwc
+    torch.manual_seed(C)
+    x = _bf(torch.randn(5, 6, 7, C, device="cuda") * 1.7).requires_grad_(True)
+    x[0, 0, 0].data.zero_()                                   # all-zero pixel: finite forward and backward
+    xn, a = nhwc.pixnorm_silu(x)
+    g1, g2 = _bf(torch.randn_like(xn)), _bf(torch.randn_like(a))
+    (xn.float() * g1.float()).sum().backward(retain_graph=True)
+    gx_only_xn = x.grad.clone(); x.grad = None
+    ((xn.float() * g1.float()).sum() + (a.float() * g2.float()).sum()).backward()
+    xr = x.detach().float().requires_grad_(True)
+    xnr = O.normalize(xr, dim=[-1])
+    ar = O.mp_silu(xnr)
+    ((xnr * g1.float()).sum() + (ar * g2.float()).sum()).backward()
+    assert torch.isfinite(x.grad).all() and torch.isfinite(gx_only_xn).all()
+    assert rel_l2(xn.float(), xnr.detach()) < 4e-3 and rel_l2(a.float(), ar.detach()) < 4e-3   # bf16 output rounding
+    assert rel_l2(x.grad.float(), xr.grad) < 6e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,with_gain", [(32, True), (64, True), (128, True), (96, False)])
+def test_nhwc_gain_silu(C, with_gain):
+    from hdmoe_b200 import nhwc
+    torch.manual_seed(C)
+    z = _bf(torch.randn(6, 9, 5, C, device="cuda") * 2).requires_grad_(True)
+    gain = (1 + 0.3 * torch.randn(6, C, device="cuda")).requires_grad_(True) if with_gain else None
+    y = nhwc.gain_silu(z, gain)
+    g = _bf(torch.randn_like(y))
+    (y.float() * g.float()).sum().backward()
+    zr = z.detach().float().requires_grad_(True)
+    gr = gain.detach().clone().requires_grad_(True) if with_gain else None
+    yr = O.mp_silu(zr * gr[:, None, None, :]) if with_gain else O.mp_silu(zr)
+    (yr * g.float()).sum().backward()
+    assert rel_l2(y.float(), yr.detach()) < 4e-3
+    assert rel_l2(z.grad.float(), zr.grad) < 6e-3
+    if with_gain:
+        assert rel_l2(gain.grad, gr.grad) < 2e-3            # fp32 accumulation over bf16 inputs
+
+
+@pytest.mark.gpu
+def test_nhwc_sum_cat_layouts():
+    from hdmoe_b200 import nhwc
+    torch.manual_seed(0)
+    x = _bf(torch.randn(3, 8, 8, 64, device="cuda")).requires_grad_(True)
+    y = _bf(torch.randn(3, 8, 8, 64, device="cuda")).requires_grad_(True)
+    b = _bf(torch.randn(3, 8, 8, 32, device="cuda")).requires_grad_(True)
+    s = nhwc.mp_sum(x, y, 0.3)
+    c = nhwc.mp_cat(s, b, 0.5)
+    g = _bf(torch.randn_like(c))
+    (c.float() * g.float()).sum().backward()
+    xr, yr, br = (t.detach().float().requires_grad_(True) for t in (x, y, b))
+    sr = O.mp_sum(xr, yr, t=0.3)
+    cr = O.mp_cat(_bf(sr).float().detach() + (sr - sr.detach()), br, dim=3, t=0.5)     # same bf16 rounding point, fp32 grads
+    (cr * g.float()).sum().backward()
+    assert rel_l2(s.float(), sr.detach()) < 4e-3 and rel_l2(c.float(), cr.detach()) < 4e-3
+    for a_, r_ in ((x, xr), (y, yr), (b, br)):
+        assert rel_l2(a_.grad.float(), r_.grad) < 6e-3
+    # layout changes are exact (pure data movement + ones channel + zero padding)
+    rows = _bf(torch.randn(5, 4, 6, 10, device="cuda")).requires_grad_(True)          # ragged: HW=60 not % 32
+    n = nhwc.rows_to_nhwc(rows, 64)
+    assert torch.equal(n[..., :4], rows.detach().permute(0, 2, 3, 1)) and bool((n[..., 4] == 1).all()) and bool((n[..., 5:] == 0).all())
+    gn = _bf(torch.randn_like(n))
+    n.backward(gn)
+    assert torch.equal(rows.grad, gn[..., :4].permute(0, 3, 1, 2))
+    z = _bf(torch.randn(5, 6, 10, 32, device="cuda")).requires_grad_(True)
+    r = nhwc.nhwc_to_rows(z)
+    assert r.is_contiguous() and torch.equal(r, z.detach().permute(0, 3, 1, 2))
+    gr = _bf(torch.randn_like(r))
+    r.backward(gr)
+    assert torch.equal(z.grad, gr.permute(0, 2, 3, 1))
