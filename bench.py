@@ -227,6 +227,7 @@ def run_ours(args):
 
                 class _Outer:
                     static = inner.static
+                    prefetch, commit = inner.prefetch, inner.commit
 
                     def __call__(self, batch=None):
                         loss = inner(batch)
@@ -286,13 +287,23 @@ def run_ours(args):
     # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, all inside the timed region
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     e2e_steps = max(3, min(args.steps, 10))
+    if graphed is not None:
+        graphed.prefetch(host)                       # untimed: allocates the staging set
+        graphed.commit()
+        torch.cuda.synchronize()
     barrier(world)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     loss_host = 0.0
-    for _ in range(e2e_steps):
+    if graphed is not None:
+        graphed.prefetch(host)                       # step 0's H2D copy (inside the timed region)
+    for i in range(e2e_steps):
         if graphed is not None:
-            loss_host = float(graphed(host).item())  # H2D into the static inputs, replay, D2H read of the loss
+            # every step's inputs come from pinned host memory; step i+1's H2D copy overlaps step i's replay
+            graphed.commit()
+            if i + 1 < e2e_steps:
+                graphed.prefetch(host)
+            loss_host = float(graphed(None).item())  # replay, D2H read of the loss
         else:
             b = {k: v.to(device, non_blocking=True) for k, v in host.items()}
             loss_host = float(step(b).item())        # D2H read of the step result

@@ -29,6 +29,11 @@ from . import nhwc
 from . import ops
 
 EPS = 1e-4
+_WGRAD_STREAM = [True]      # weight-gradient launches on a side stream (off the data-gradient critical path)
+
+
+def set_wgrad_stream(enabled: bool) -> None:
+    _WGRAD_STREAM[0] = bool(enabled)
 
 
 def _round_up(x, k):
@@ -85,7 +90,7 @@ class _GConvFn(torch.autograd.Function):
                                layer.ks, layer.wrow_t)
             if layer.cin_rows < layer.cin_pad:
                 dx = F.pad(dx, (0, layer.cin_pad - layer.cin_rows))
-        runner.weight_grad(layer, x, dy)
+        runner.weight_grad_async(layer, x, dy)
         return dx, torch.zeros_like(ctx.runner.token_like), None, None
 
 
@@ -155,6 +160,7 @@ class GroupedUnetExperts:
         self.emb_size = e0.emb_size
         self.has_text = e0.map_text is not None
         self._built_for = None
+        self._wg_stream, self._wg_pending = None, False
         self.plan = None
         self.token_like = None
 
@@ -275,6 +281,9 @@ class GroupedUnetExperts:
         """Accumulated operand gradients -> master-weight gradients, ONE multi-tensor launch.  The returned
         gradients are views of a persistent buffer (call optimizer.zero_grad(set_to_none=True), the default)."""
         dev = self.plan.counts.device
+        if self._wg_pending:
+            torch.cuda.current_stream().wait_stream(self._wg_stream)
+            self._wg_pending = False
         for buf, g in ((self.g_noise, g_noise), (self.g_text, g_text), (self.g_emb, g_emb)):
             if g is None:
                 buf.zero_()
@@ -299,6 +308,22 @@ class GroupedUnetExperts:
         """layer.dw (fp32, tap-major blocks) += grouped weight gradient: one tcgen05 launch for all experts."""
         p = self.plan
         ops.gconv_wgrad_raw(x, dy, layer.dw, p.row_expert, p.n_rows_dev, layer.ks, layer.wrow)
+
+    def weight_grad_async(self, layer, x, dy):
+        """Weight gradient on a side stream: nothing on the data-gradient chain depends on it; the join is in
+        _run_prep_backward (the W-PREP backward node runs after every convolution's backward)."""
+        if not _WGRAD_STREAM[0]:
+            return self.weight_grad(layer, x, dy)
+        cur = torch.cuda.current_stream()
+        if self._wg_stream is None:
+            self._wg_stream = torch.cuda.Stream(device=x.device)
+        side = self._wg_stream
+        side.wait_stream(cur)
+        x.record_stream(side)
+        dy.record_stream(side)
+        with torch.cuda.stream(side):
+            self.weight_grad(layer, x, dy)
+        self._wg_pending = True
 
     # ------------------------------------------------------------------------------------------ forward
     def _conv(self, x, li, token, training, scale=None, act=0, residual=None, res_a=0.0, res_b=1.0):

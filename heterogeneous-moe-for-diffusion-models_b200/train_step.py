@@ -19,6 +19,7 @@ class GraphedTrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss: Optional[torch.Tensor] = None
         self.warmup = warmup
+        self._stage = self._copy_stream = self._staged = self._stage_free = None
 
     def capture(self) -> "GraphedTrainStep":
         s = torch.cuda.Stream()
@@ -37,6 +38,29 @@ class GraphedTrainStep:
     def load(self, batch: Dict[str, torch.Tensor]) -> None:
         for k, v in batch.items():
             self.static[k].copy_(v, non_blocking=True)
+
+    # -- input pipeline: the next batch's host->device copy runs on a copy stream beside the current replay -------
+    def prefetch(self, host_batch: Dict[str, torch.Tensor]) -> None:
+        """Start the asynchronous H2D copy of the NEXT step's (pinned) host batch into a staging set."""
+        if self._stage is None:
+            self._stage = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._staged, self._stage_free = torch.cuda.Event(), torch.cuda.Event()
+            self._stage_free.record()
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)                  # the previous commit has drained the staging set
+        with torch.cuda.stream(cs):
+            for k, v in host_batch.items():
+                self._stage[k].copy_(v, non_blocking=True)
+            self._staged.record(cs)
+
+    def commit(self) -> None:
+        """Make the prefetched batch the graph's static input (device-to-device, after the H2D copy finished)."""
+        main = torch.cuda.current_stream()
+        main.wait_event(self._staged)
+        for k, v in self._stage.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self._stage_free.record(main)
 
     def __call__(self, batch: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
         if batch is not None:
