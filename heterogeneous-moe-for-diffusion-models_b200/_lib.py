@@ -64,6 +64,8 @@ PROTOTYPES = {
     "hdmoe_nhwc_to_nchw": (_i, [_p, _p, _i64, _i, _i, _i64, _p]),
     "hdmoe_attn_d4_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "hdmoe_attn_d4_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "hdmoe_attn_d4_tc_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
+    "hdmoe_attn_d4_tc_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "hdmoe_wprep_fwd_resident": (_i, [_p, _i, _i, _i, _p]),
     "hdmoe_wprep_bwd_multi_resident": (_i, [_p, _i, _i, _p]),
     "hdmoe_wprep_bwd_multi": (_i, [_p, _p, _i, _p]),

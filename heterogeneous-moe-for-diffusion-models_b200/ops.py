@@ -572,6 +572,20 @@ def gconv_wgrad_raw(x, dy, dw, row_expert, n_rows_dev, ksizes, wrows):
 # ----------------------------------------------------------------------------------------------------
 # (7) trunk attention, head_dim = 4
 # ----------------------------------------------------------------------------------------------------
+# attention implementation: "tc" = warp-MMA tensor-core kernels (csrc/attention_tc.cu), "cc" = CUDA-core kernels
+_ATTN_IMPL = ["tc"]
+
+
+def set_attention_impl(impl: str) -> None:
+    assert impl in ("tc", "cc")
+    _ATTN_IMPL[0] = impl
+
+
+def _attn_split_p() -> int:
+    """Strict fp32 (p and dS split into hi + lo) unless TF32 matmuls are enabled, like the library matmuls."""
+    return 0 if torch.backends.cuda.matmul.allow_tf32 else 1
+
+
 class _AttnD4(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, heads, scale):
@@ -582,23 +596,32 @@ class _AttnD4(torch.autograd.Function):
         assert Cc == heads * 4 and k.shape == (B, Sk, Cc) and v.shape == (B, Sk, Cc)
         o = torch.empty_like(q)
         lse = torch.empty(B, heads, Sq, dtype=torch.float32, device=q.device)
-        L.check(L.lib().hdmoe_attn_d4_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), B, Sq, Sk, heads, float(scale), _st()),
-                "attn_d4_fwd")
+        impl, split = _ATTN_IMPL[0], _attn_split_p()
+        if impl == "tc":
+            L.check(L.lib().hdmoe_attn_d4_tc_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), B, Sq, Sk, heads, float(scale), split,
+                                                 _st()), "attn_d4_tc_fwd")
+        else:
+            L.check(L.lib().hdmoe_attn_d4_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), B, Sq, Sk, heads, float(scale), _st()),
+                    "attn_d4_fwd")
         ctx.save_for_backward(q, k, v, o, lse)
-        ctx.meta = (heads, float(scale))
+        ctx.meta = (heads, float(scale), impl, split)
         return o
 
     @staticmethod
     def backward(ctx, dO):
         q, k, v, o, lse = ctx.saved_tensors
-        heads, scale = ctx.meta
+        heads, scale, impl, split = ctx.meta
         dO = _f32c(dO)
         B, Sq, _ = q.shape
         Sk = k.shape[1]
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         Dbuf = torch.empty_like(lse)
-        L.check(L.lib().hdmoe_attn_d4_bwd(_p(q), _p(k), _p(v), _p(o), _p(dO), _p(lse), _p(dq), _p(dk), _p(dv), _p(Dbuf),
-                                          B, Sq, Sk, heads, scale, _st()), "attn_d4_bwd")
+        if impl == "tc":
+            L.check(L.lib().hdmoe_attn_d4_tc_bwd(_p(q), _p(k), _p(v), _p(o), _p(dO), _p(lse), _p(dq), _p(dk), _p(dv),
+                                                 _p(Dbuf), B, Sq, Sk, heads, scale, split, _st()), "attn_d4_tc_bwd")
+        else:
+            L.check(L.lib().hdmoe_attn_d4_bwd(_p(q), _p(k), _p(v), _p(o), _p(dO), _p(lse), _p(dq), _p(dk), _p(dv), _p(Dbuf),
+                                              B, Sq, Sk, heads, scale, _st()), "attn_d4_bwd")
         return dq, dk, dv, None, None
 
 

@@ -218,6 +218,17 @@ int hdmoe_attn_d4_bwd(const float* q, const float* k, const float* v, const floa
                       const float* lse, float* dq, float* dk, float* dv, float* Dbuf, int B, int Sq, int Sk,
                       int heads, float scale, hdmoe_stream_t stream);
 
+/* Tensor-core variant (csrc/attention_tc.cu): warp-level m16n8k8 TF32 MMAs with split (hi + lo) operands for the
+ * logits and for V / K / Q / dO, probabilities kept in registers.  split_p != 0 also splits p and dS into hi + lo
+ * (fp32-grade results, used when TF32 matmuls are disabled); split_p == 0 rounds them to TF32 (the setting of the
+ * reference's own run with torch.backends.cuda.matmul.allow_tf32).  Same tensors and saved values as above; any
+ * number of heads. */
+int hdmoe_attn_d4_tc_fwd(const float* q, const float* k, const float* v, float* o, float* lse, int B, int Sq, int Sk,
+                         int heads, float scale, int split_p, hdmoe_stream_t stream);
+int hdmoe_attn_d4_tc_bwd(const float* q, const float* k, const float* v, const float* o, const float* dO,
+                         const float* lse, float* dq, float* dk, float* dv, float* Dbuf, int B, int Sq, int Sk,
+                         int heads, float scale, int split_p, hdmoe_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (8) Fused NHWC bf16 elementwise kernels of the U-Net expert block -- replace the elementwise ATen chains of
  *     Unet_block.forward (models/model_components.py:232-253) and of Unet_expert.forward (:416, :428):

@@ -1,0 +1,60 @@
+"""Kernel timeline of ONE replay of the captured train step (torch.profiler / CUPTI timestamps, per stream):
+prints per-bin concurrency and the dominant kernels, to find the critical path.  Guidance only."""
+import sys, collections, re, torch
+sys.path.insert(0, '.')
+import bench, hdmoe_b200
+from hdmoe_b200.utils import EDM_LOSS
+from hdmoe_b200.train_step import GraphedTrainStep
+from torch.profiler import profile, ProfilerActivity
+dev = torch.device("cuda")
+torch.backends.cuda.matmul.allow_tf32 = True
+torch.backends.cudnn.allow_tf32 = True
+hdmoe_b200.set_expert_dtype(torch.bfloat16)
+B = 256
+model = bench.build_model(1, dev); model.train()
+crit = EDM_LOSS(**bench.LOSS)
+params = list(model.parameters())
+opt = torch.optim.AdamW(params, lr=5e-4, fused=True, capturable=True)
+b = {k: v.to(dev) for k, v in bench.synth_batch(B, 32, 0, dev).items()}
+def step(b):
+    out = model(x=b["x"], sigma=b["sigma"], text_emb=b["text"], Unet_router_mask=b["um"], Vit_router_mask=b["vm"], zeta=2.0, return_log_var=True)
+    loss = crit(b["sigma"], b["x0"], b["sigma"], out)
+    opt.zero_grad(set_to_none=True)
+    loss["loss"].backward()
+    torch.nn.utils.clip_grad_norm_(params, 1.0)
+    opt.step()
+    return loss["loss"]
+g = GraphedTrainStep(step, b, warmup=3).capture()
+for _ in range(3): g(None)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    g(None); torch.cuda.synchronize()
+evs = []
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        n = re.sub(r'<.*', '', ev.name); n = re.sub(r'\(.*', '', n); n = n.replace("void ", "").replace("at::native::", "")[:40]
+        evs.append((ev.time_range.start, ev.time_range.end, getattr(ev, "device_resource_id", getattr(ev, "device_index", 0)), n))
+evs.sort()
+t0 = evs[0][0]; t1 = max(e[1] for e in evs)
+print(f"replay span {(t1 - t0)/1e3:.3f} ms, {len(evs)} kernels, sum of durations {sum(e[1]-e[0] for e in evs)/1e3:.3f} ms")
+binw = float(sys.argv[1]) if len(sys.argv) > 1 else 500.0     # us
+nb = int((t1 - t0) / binw) + 1
+for i in range(nb):
+    lo, hi = t0 + i * binw, t0 + (i + 1) * binw
+    act = [(min(e[1], hi) - max(e[0], lo), e) for e in evs if e[1] > lo and e[0] < hi]
+    busy = sum(a for a, _ in act)
+    # union coverage
+    iv = sorted((max(e[0], lo), min(e[1], hi)) for _, e in act)
+    cov = 0; cur = None
+    for a, c in iv:
+        if cur is None or a > cur[1]:
+            if cur: cov += cur[1] - cur[0]
+            cur = [a, c]
+        else:
+            cur[1] = max(cur[1], c)
+    if cur: cov += cur[1] - cur[0]
+    names = collections.Counter()
+    for a, e in act: names[e[3]] += a
+    streams = len({e[2] for _, e in act})
+    top = ", ".join(f"{k}:{v/binw:.2f}" for k, v in names.most_common(4))
+    print(f"{i*binw/1e3:6.2f} ms  cover {cov/binw:4.2f}  load {busy/binw:4.2f}  streams {streams}  n={len(act):3d} | {top}")
