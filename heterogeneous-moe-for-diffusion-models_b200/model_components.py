@@ -14,6 +14,13 @@ from . import ops
 _CHANNELS_LAST = [False]   # measured: no gain on B200 (cuDNN picks NHWC kernels either way)
 
 
+_FUSED_TRUNK = [True]       # fused GroupNorm(1)+ReLU(+pool) kernels and channels-last convolutions in Router.hard_route
+
+
+def set_router_fused_trunk(enabled: bool) -> None:
+    _FUSED_TRUNK[0] = bool(enabled)
+
+
 def set_router_channels_last(enabled: bool) -> None:
     _CHANNELS_LAST[0] = bool(enabled)
 
@@ -76,13 +83,32 @@ class Router(nn.Module):
         self.k = top_k
         self.last = None
 
+    def _fusable(self) -> bool:
+        seq = self.hard_route
+        return all(isinstance(seq[i + 1], nn.GroupNorm) and seq[i + 1].num_groups == 1
+                   and ops.gn1_relu_supported(seq[i + 1].num_channels) for i in (0, 3, 6))
+
+    def _fused_trunk(self, x: torch.Tensor) -> torch.Tensor:
+        """hard_route with channels-last library convolutions (no layout-conversion kernels) and the fused
+        GroupNorm(1) + ReLU (+ average pool for the last layer) kernels; same modules, parameters and result."""
+        seq = self.hard_route
+        h = x.contiguous(memory_format=torch.channels_last)
+        for i in (0, 3, 6):
+            h = seq[i](h).contiguous(memory_format=torch.channels_last)
+            gn = seq[i + 1]
+            h = ops.gn1_relu(h, gn.weight, gn.bias, gn.eps, pool=(i == 6))
+        B, Cn = h.shape
+        return seq[10](h.view(B, Cn, 1, 1)).reshape(B, Cn)
+
     def forward(self, x: torch.Tensor, time_emb: torch.Tensor, mask: Optional[torch.Tensor] = None,
                 zeta: Optional[float] = 1e-2, noise: Optional[torch.Tensor] = None):
         B = x.shape[0]
-        if x.is_cuda and _CHANNELS_LAST[0]:
-            # NHWC trunk: the library convolutions run channels-last natively (no NCHW<->NHWC conversion kernels)
-            x = x.contiguous(memory_format=torch.channels_last)
-        pooled = self.hard_route(x).reshape(B, -1).float()
+        if x.is_cuda and x.dtype == torch.float32 and _FUSED_TRUNK[0] and self._fusable():
+            pooled = self._fused_trunk(x).float()
+        else:
+            if x.is_cuda and _CHANNELS_LAST[0]:
+                x = x.contiguous(memory_format=torch.channels_last)
+            pooled = self.hard_route(x).reshape(B, -1).float()
         if time_emb.ndim == 3:
             time_emb = time_emb.squeeze(1)
         cond = self.time_linear(m.mp_silu(time_emb)).float()

@@ -572,6 +572,50 @@ def gconv_wgrad_raw(x, dy, dw, row_expert, n_rows_dev, ksizes, wrows):
 # ----------------------------------------------------------------------------------------------------
 # (7) trunk attention, head_dim = 4
 # ----------------------------------------------------------------------------------------------------
+class _GN1Relu(torch.autograd.Function):
+    """relu(group_norm(x, 1 group)) [+ mean over H, W] on channels-last fp32 x (csrc/gn_relu.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, pool):
+        _cuda(x, gamma, beta)
+        B, Cn, H, W = x.shape
+        if x.dtype != torch.float32 or not x.is_contiguous(memory_format=torch.channels_last):
+            raise RuntimeError("gn1_relu: x must be channels-last float32")
+        gamma, beta = _f32c(gamma), _f32c(beta)
+        stats = torch.empty(B, 2, dtype=torch.float32, device=x.device)
+        y = None if pool else torch.empty_like(x)
+        pooled = torch.empty(B, Cn, dtype=torch.float32, device=x.device) if pool else None
+        L.check(L.lib().hdmoe_gn1_relu_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(pooled), _p(stats), B, H * W, Cn,
+                                           float(eps), _st()), "gn1_relu_fwd")
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.pool = pool
+        return pooled if pool else y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, beta, stats = ctx.saved_tensors
+        B, Cn, H, W = x.shape
+        g = g.float()
+        g = g.contiguous() if ctx.pool else g.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        parts = torch.empty(2, B, Cn, dtype=torch.float32, device=x.device)
+        L.check(L.lib().hdmoe_gn1_relu_bwd(_p(x), _p(gamma), _p(beta), _p(stats), None if ctx.pool else _p(g),
+                                           _p(g) if ctx.pool else None, _p(dx), _p(parts[0]), _p(parts[1]), B, H * W, Cn,
+                                           _st()), "gn1_relu_bwd")
+        sums = parts.sum(dim=1)
+        return dx, sums[0], sums[1], None, None
+
+
+def gn1_relu(x, gamma, beta, eps: float = 1e-5, pool: bool = False):
+    """ReLU(GroupNorm(1, C)(x)) for channels-last fp32 x [B, C, H, W]; pool=True returns the [B, C] spatial mean
+    instead (the tail of Router.hard_route, models/model_components.py:92-103)."""
+    return _GN1Relu.apply(x, gamma, beta, eps, pool)
+
+
+def gn1_relu_supported(channels: int) -> bool:
+    return channels % 4 == 0 and 1024 % (channels // 4) == 0
+
+
 # attention implementation: "tc" = warp-MMA tensor-core kernels (csrc/attention_tc.cu), "cc" = CUDA-core kernels
 _ATTN_IMPL = ["tc"]
 

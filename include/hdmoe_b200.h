@@ -230,6 +230,19 @@ int hdmoe_attn_d4_tc_bwd(const float* q, const float* k, const float* v, const f
                          int heads, float scale, int split_p, hdmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (9) Router trunk normalisation: GroupNorm(num_groups = 1, C) + ReLU [+ AdaptiveAvgPool2d((1,1))] of
+ *     Router.hard_route (models/model_components.py:92-103) on channels-last fp32 activations x [B, HW, C].
+ *     fwd: y (may be NULL) = relu(gn(x)), pooled (may be NULL) [B, C] = mean over HW of y, stats [B, 2] = (mean, rstd).
+ *     bwd: exactly one of dy [B, HW, C] / dpooled [B, C]; dx [B, HW, C]; per-sample partials dgamma_part, dbeta_part
+ *     [B, C] (the caller sums over B: deterministic).  C / 4 must divide 1024.
+ * ---------------------------------------------------------------------------------------------- */
+int hdmoe_gn1_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* pooled, float* stats, int B,
+                       int HW, int C, float eps, hdmoe_stream_t stream);
+int hdmoe_gn1_relu_bwd(const float* x, const float* gamma, const float* beta, const float* stats, const float* dy,
+                       const float* dpooled, float* dx, float* dgamma_part, float* dbeta_part, int B, int HW, int C,
+                       hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (8) Fused NHWC bf16 elementwise kernels of the U-Net expert block -- replace the elementwise ATen chains of
  *     Unet_block.forward (models/model_components.py:232-253) and of Unet_expert.forward (:416, :428):
  *       pixnorm_silu : xn = x / (1e-4 + ||x||_C / sqrt(C)),  a = mp_silu(xn)            (:238, :240)

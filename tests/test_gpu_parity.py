@@ -694,3 +694,27 @@ def test_nhwc_sum_cat_layouts():
     gr = _bf(torch.randn_like(r))
     r.backward(gr)
     assert torch.equal(z.grad, gr.permute(0, 2, 3, 1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,pool", [(64, False), (128, False), (128, True), (8, True)])
+def test_gn1_relu_matches_torch(C, pool):
+    """Router trunk GroupNorm(1, C) + ReLU (+ AdaptiveAvgPool2d) kernel vs torch ops in float64 (fwd + bwd)."""
+    import torch.nn.functional as F
+    from hdmoe_b200 import ops
+    torch.manual_seed(C)
+    B, H, W = 5, 12, 8
+    x = (torch.randn(B, C, H, W, device="cuda") * 1.3 + 0.4).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(C, device="cuda")).requires_grad_(True)
+    beta = (0.3 * torch.randn(C, device="cuda")).requires_grad_(True)
+    out = ops.gn1_relu(x, gamma, beta, 1e-5, pool=pool)
+    gy = torch.randn_like(out)
+    (out * gy).sum().backward()
+    xr, gr, br = (t.detach().double().requires_grad_(True) for t in (x, gamma, beta))
+    ref = F.relu(F.group_norm(xr, 1, gr, br, 1e-5))
+    if pool:
+        ref = ref.mean(dim=(2, 3))
+    (ref * gy.double()).sum().backward()
+    assert rel_l2(out, ref.detach()) < 1e-5
+    assert rel_l2(x.grad, xr.grad) < 2e-5
+    assert rel_l2(gamma.grad, gr.grad) < 2e-5 and rel_l2(beta.grad, br.grad) < 2e-5
