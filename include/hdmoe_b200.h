@@ -230,6 +230,24 @@ int hdmoe_attn_d4_tc_bwd(const float* q, const float* k, const float* v, const f
                          int heads, float scale, int split_p, hdmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (10) Fused DiffiT block of the ViT experts: Vit_block.forward (models/model_components.py:525-562) including its
+ *      MP_Attention self-attention (models/model_internals.py:354-409), for emb 32, 8 heads, time_dim 64, hidden
+ *      128, <= 64 tokens.  One launch runs every expert of the layer: row r uses expert row_expert[r] (< 0: row
+ *      unused, output zero).  tok_in / tok_out [rows][64][32] fp32 (tokens beyond the expert's count ignored / zero),
+ *      time [rows][64].  w_hat: prepared (normalised, gain-scaled) MP_Conv weights, expert e's block at float offset
+ *      w_off[e] in the order linear1, q, k, v, out_proj [32x32 each], q_time, k_time, v_time [32x64], linear2
+ *      [128x32], linear3 [32x128].  aux: expert e's block at a_off[e]: GN (w, b), norm1 (w, b), norm2 (w, b), final
+ *      LayerNorm (w, b) [32 each], rel_pos_bias [8][S_e][S_e].  final_ln: also apply the final LayerNorm
+ *      (Vit_expert.norm, :698).  w_off / a_off / tokens are HOST arrays of n_experts (<= 8) entries.
+ *      bwd: recomputes the block from tok_in; d_w_part / d_aux_part are [n_slices][w_total] / [n_slices][aux_total]
+ *      scratch (zeroed by the kernel); slice c accumulates expert c % n_experts; the caller sums the slices of each
+ *      expert.  counts_off: device [n_experts + 1] exclusive row offsets of the expert-major rows.
+ * ---------------------------------------------------------------------------------------------- */
+int hdmoe_vit_block_fwd(const float* tok_in, const float* time, const int32_t* row_expert, const float* w_hat,
+                        const float* aux, const int64_t* w_off, const int64_t* a_off, const int32_t* tokens, int n_experts,
+                        int64_t rows, int final_ln, float* tok_out, hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (9) Router trunk normalisation: GroupNorm(num_groups = 1, C) + ReLU [+ AdaptiveAvgPool2d((1,1))] of
  *     Router.hard_route (models/model_components.py:92-103) on channels-last fp32 activations x [B, HW, C].
  *     fwd: y (may be NULL) = relu(gn(x)), pooled (may be NULL) [B, C] = mean over HW of y, stats [B, 2] = (mean, rstd).

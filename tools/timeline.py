@@ -58,3 +58,18 @@ for i in range(nb):
     streams = len({e[2] for _, e in act})
     top = ", ".join(f"{k}:{v/binw:.2f}" for k, v in names.most_common(4))
     print(f"{i*binw/1e3:6.2f} ms  cover {cov/binw:4.2f}  load {busy/binw:4.2f}  streams {streams}  n={len(act):3d} | {top}")
+print("\n--- per stream ---")
+by = collections.defaultdict(list)
+for e in evs: by[e[2]].append(e)
+for sid, lst in sorted(by.items(), key=lambda kv: kv[1][0][0]):
+    busy = sum(e[1] - e[0] for e in lst)
+    names = collections.Counter()
+    for e in lst: names[e[3]] += e[1] - e[0]
+    print(f"stream {sid}: n={len(lst)} first {(lst[0][0]-t0)/1e3:.2f} ms last {(max(e[1] for e in lst)-t0)/1e3:.2f} ms busy {busy/1e3:.2f} ms | " + ", ".join(f"{k}:{v/1e3:.2f}" for k, v in names.most_common(5)))
+    # activity windows (gaps > 300 us split)
+    wins = []; cur = [lst[0][0], lst[0][1], lst[0][1] - lst[0][0]]
+    for e in lst[1:]:
+        if e[0] - cur[1] > 300: wins.append(cur); cur = [e[0], e[1], 0.0]
+        cur[1] = max(cur[1], e[1]); cur[2] += e[1] - e[0]
+    wins.append(cur)
+    print("    windows: " + "  ".join(f"[{(a-t0)/1e3:.2f}-{(b-t0)/1e3:.2f} busy {c/1e3:.2f}]" for a, b, c in wins))
