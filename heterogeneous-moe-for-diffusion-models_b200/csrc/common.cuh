@@ -13,6 +13,8 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+constexpr int kSchedSlots = 256;
+int32_t* sched_slot(cudaStream_t st);   // per-(device, stream) {next tile, finished CTAs} counter pair, see core.cu
 
 #define HDMOE_CHECK_ARG(cond, ...)                \
     do {                                          \

@@ -11,12 +11,20 @@
 //     adesc.start = base + (r*Wp + s + 128*mt) * rowbytes.  Hardware fact (tools/umma_probe.cu, B200): a K-major
 //     swizzled operand may start at any 128-byte row with base_offset = 0 -- the swizzle acts on absolute
 //     shared-memory address bits;
-//   * M-tiles cover 128 consecutive positions; positions in the padding columns produce garbage rows that the
-//     epilogue drops (cost: Wp/W and 128-rounding, 67-92 % MMA efficiency, far cheaper than the re-reads);
-//   * weights stream through a small ring, one [Cout x KC] box per (tap, chunk), reused by all M-tiles.
+//   * M-tiles cover 128 consecutive positions of the flattened padded image [0, H*Wp); positions in the padding
+//     columns produce garbage rows that the epilogue drops.  A tile is a run of <= 3 M-tiles that need NOT start on
+//     an image row (32x32, k=5: 1152 positions = exactly 9 M-tiles = 3 tiles), so every issuer warp is busy on
+//     every tile -- a lone M-tile would run at the single-thread issue rate (~103 cycles / MMA, tools/umma_rate.cu);
+//   * weights stream through a small ring, one [Cout x KC] box per (tap, chunk), reused by all M-tiles;
+//   * the epilogue goes TMEM -> registers -> global with 32-byte vector stores (a thread owns one position's
+//     channel vector = one contiguous NHWC line).  It must NOT touch shared memory: the SS-mode MMAs at N <= 64
+//     already consume the full 128 B/clk of shared-memory bandwidth, and an smem-staged epilogue ran 3x slower
+//     under them (15 k cycles per tile, trace in profiles/) while slowing the MMAs from 48 to 60 cycles;
+//   * tiles are handed out dynamically (heavy kernel sizes first) from a self-resetting global counter: a 5x5 tile
+//     costs 2.8x a 3x3 tile, static striding left 16 % of the SM-cycles idle.
 //
 // Everything else follows v1: per-tile expert lookup (kernel size, weight block) for the grouped /
-// heterogeneous case, warp-specialised roles (TMA producer, single-thread MMA issuer, 4 epilogue warps),
+// heterogeneous case, warp-specialised roles (TMA producer, MMA issuers, 4 epilogue warps),
 // double-buffered TMEM accumulators, fused epilogue (scale, mp_silu, mp_sum residual), NHWC bf16 output.
 #include "tc.cuh"
 #include "../../include/hdmoe_gemm.h"
@@ -25,7 +33,9 @@ namespace hdmoe {
 
 #ifdef HDMOE_G2_TRACE
 __device__ long long g2_trace[148 * 64];
-#define G2T(slot) do { if (blockIdx.x < 148 && tcount < 8) g2_trace[blockIdx.x * 64 + tcount * 8 + (slot)] = clock64(); } while (0)
+__device__ __forceinline__ long long g2_gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define G2T(slot) do { if (blockIdx.x < 148 && tcount < 8) { g2_trace[blockIdx.x * 64 + tcount * 8 + (slot)] = clock64(); \
+    if ((slot) == 0) g2_trace[blockIdx.x * 64 + tcount * 8 + 6] = g2_gtime(); if ((slot) == 5) g2_trace[blockIdx.x * 64 + tcount * 8 + 7] = g2_gtime(); } } while (0)
 #else
 #define G2T(slot) do { } while (0)
 #endif
@@ -35,7 +45,8 @@ constexpr int kG2Issuers = 3;      // MMA-issuer warps, one per M-tile accumulat
 constexpr int kG2Threads = 32 * (1 + kG2Issuers + 4);
 constexpr int kG2MaxE = HDMOE_MAX_EXPERTS;
 constexpr int kG2Classes = 4;     // distinct kernel sizes per launch
-constexpr int kG2MaxStrips = 32;
+constexpr int kG2RowCache = 4096; // rows whose expert id is staged in shared memory (larger launches read global memory)
+constexpr int kG2Queue = 16;      // depth of the tile-id queue between the scheduler (producer) and the other roles
 
 struct GConv2Params {
     int n_tiles, smax;                // tiles = cap_rows * smax (strips per sample, max over classes)
@@ -52,10 +63,15 @@ struct GConv2Params {
     int act;
     int32_t wrow[kG2MaxE];
     uint8_t kclass[kG2MaxE];
-    // per kernel-size class
+    int32_t* sched;                   // [0] next tile, [1] finished CTAs (self-resetting)
+    // per kernel-size class: tile j covers M-tiles [j*mt_base + min(j, mt_extra), +mt_base + (j < mt_extra))
     int32_t ksize[kG2Classes], wp[kG2Classes], box_bytes[kG2Classes];
-    uint8_t nstrips[kG2Classes];
-    uint8_t strip_h0[kG2Classes][kG2MaxStrips], strip_sh[kG2Classes][kG2MaxStrips];
+    int32_t ntile[kG2Classes], mt_base[kG2Classes], mt_extra[kG2Classes];
+};
+
+struct G2Tile {
+    int r, j, e, kc;                  // row (sample), tile of the sample, expert, kernel-size class
+    int mt_n, p0, h0, c0;             // M-tiles, first position, its image row / offset inside that row's box
 };
 
 template <int KC, int N>
@@ -67,9 +83,89 @@ struct Conv2Cfg {
     static constexpr int B_STAGE = TPS * B_TAP;
     static constexpr int A_STAGES = 2;
     static constexpr int B_STAGES = 4;
+    static constexpr int EPI_NB = (N % 64 == 0) ? 2 : 1;      // 32-column accumulator loads in flight per epilogue thread
     static constexpr int TMEM_NEED = 2 * MT_MAX * N;
     static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
 };
+
+// 32-byte global accesses (sm_100: LDG/STG.256)
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t* v) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+        "%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Epilogue of one tile for one thread: position q0 + 128*mt of the flattened padded image, accumulator columns
+// [tc0 + mt*N, +N).  TMEM -> registers -> (scale, mp_silu, mp_sum residual) -> bf16 -> 32-byte global stores.
+template <int N, bool SC, bool ACT, bool RES>
+__device__ __forceinline__ void g2_epilogue(const GConv2Params& p, const G2Tile& t, int q0, uint32_t tc0) {
+    const int Wp = p.wp[t.kc];
+    const float* sc = SC ? p.scale + (size_t)t.r * N : nullptr;
+    for (int mt = 0; mt < t.mt_n; ++mt) {
+        // this thread's position -> output pixel (or a padding column / the tail past the image)
+        const int pa = q0 + mt * 128;
+        const int hl = pa / Wp, w = pa - hl * Wp;
+        const bool valid = hl < p.H && w < p.W;
+        const size_t go = (((size_t)t.r * p.H + (size_t)hl) * p.W + w) * N;
+        const uint32_t tcol = tc0 + (uint32_t)(mt * N);
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32_issue(tcol + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {                      // 16 channels = one 32-byte store
+                uint32_t packed[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    float a = __uint_as_float(v[g * 16 + 2 * u]), b = __uint_as_float(v[g * 16 + 2 * u + 1]);
+                    if (SC) {
+                        const float2 s2 = __ldg(reinterpret_cast<const float2*>(sc + c0 + g * 16 + 2 * u));
+                        a *= s2.x;
+                        b *= s2.y;
+                    }
+                    if (ACT) {
+                        a = __fdividef(a, 1.f + __expf(-a)) * (1.f / 0.596f);
+                        b = __fdividef(b, 1.f + __expf(-b)) * (1.f / 0.596f);
+                    }
+                    __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
+                    packed[u] = *reinterpret_cast<uint32_t*>(&o);
+                }
+                if (valid) {
+                    if (RES) {   // mp_sum folded: out = res_a * residual + res_b * value (value rounded to bf16 first)
+                        uint32_t rr[8];
+                        ld_global_v8(p.res + go + c0 + g * 16, rr);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float v0 = __uint_as_float(packed[u] << 16), v1 = __uint_as_float(packed[u] & 0xffff0000u);
+                            const float r0 = __uint_as_float(rr[u] << 16), r1 = __uint_as_float(rr[u] & 0xffff0000u);
+                            __nv_bfloat162 o = __floats2bfloat162_rn(p.res_a * r0 + p.res_b * v0, p.res_a * r1 + p.res_b * v1);
+                            packed[u] = *reinterpret_cast<uint32_t*>(&o);
+                        }
+                    }
+                    st_global_v8(p.Y + go + c0 + g * 16, packed);
+                }
+            }
+        }
+    }
+}
 
 template <int KC, int N>
 __global__ void __launch_bounds__(kG2Threads, 1)
@@ -81,11 +177,20 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_buf = smem;                                              // A_STAGES halo buffers
     uint8_t* b_buf = smem + (size_t)Cfg::A_STAGES * p.a_stage_bytes;    // weight ring
-    uint8_t* stage_buf = b_buf + (size_t)Cfg::B_STAGES * Cfg::B_STAGE;  // epilogue staging: 4 warps x 32 rows x N bf16
-    __shared__ int32_t stage_off[4 * 32];
     __shared__ __align__(8) uint64_t a_full[Cfg::A_STAGES], a_empty[Cfg::A_STAGES], b_full[Cfg::B_STAGES],
-        b_empty[Cfg::B_STAGES], t_full[2], t_empty[2];
+        b_empty[Cfg::B_STAGES], t_full[2], t_empty[2], q_full[kG2Queue], q_empty[kG2Queue];
+    __shared__ int32_t tile_q[kG2Queue];
     __shared__ uint32_t tmem_base_s;
+    // expert of every row, staged once: each role decodes every tile, and a global load per tile (~700 cycles of L2
+    // latency in front of the first MMA of the tile) showed up as a 1 100-cycle gap between tiles
+    __shared__ int8_t row_e_s[kG2RowCache];
+    const int cap_rows = p.n_tiles / p.smax;
+    const bool rows_cached = cap_rows <= kG2RowCache;
+    if (rows_cached)
+        for (int r = threadIdx.x; r < cap_rows; r += kG2Threads) {
+            const int e = p.row_expert[r];
+            row_e_s[r] = (int8_t)((e < 0 || e >= p.n_experts) ? -1 : e);
+        }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -101,6 +206,10 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
             mb_init(&t_full[a], kG2Issuers);
             mb_init(&t_empty[a], 4);
         }
+        for (int s = 0; s < kG2Queue; ++s) {
+            mb_init(&q_full[s], 1);
+            mb_init(&q_empty[s], kG2Issuers + 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -115,220 +224,236 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
     const uint32_t tmem_base = tmem_base_s;
     const int n_rows = *p.n_rows_dev;
 
-    // tile -> (row, strip); every role walks the same sequence and skips the same tiles
-    auto tile_at = [&](int i, int& r, int& j, int& e, int& kc) -> bool {
-        // strip-major, rows reversed inside a strip: the heavy (large-kernel) experts sit at the end of the row
-        // order and are scheduled first, and a CTA's static stride (gridDim = 148 = 4*37) does not alias with
-        // the strip index (a row-major order would hand some CTAs only the small last strips)
-        const int cap = p.n_tiles / p.smax;
-        j = i / cap;
-        r = cap - 1 - (i - j * cap);
-        e = -1;
-        kc = 0;
-        if (r >= n_rows) return false;
-        e = p.row_expert[r];
-        if (e < 0 || e >= p.n_experts) return false;
-        kc = p.kclass[e];
-        return j < p.nstrips[kc];
+    // tile id -> geometry.  Row-major with the rows reversed: the heavy (large-kernel) experts sit at the end of the
+    // expert-major row order and are handed out first (longest-processing-time-first for the dynamic scheduler).
+    auto tile_at = [&](int i, G2Tile& t) -> bool {
+        const int q = i / p.smax;
+        t.j = i - q * p.smax;
+        t.r = cap_rows - 1 - q;
+        t.e = -1;
+        t.kc = 0;
+        if (t.r >= n_rows) return false;
+        t.e = rows_cached ? (int)row_e_s[t.r] : p.row_expert[t.r];
+        if (t.e < 0 || t.e >= p.n_experts) return false;
+        t.kc = p.kclass[t.e];
+        if (t.j >= p.ntile[t.kc]) return false;
+        const int base = p.mt_base[t.kc], extra = p.mt_extra[t.kc], Wp = p.wp[t.kc];
+        t.mt_n = base + (t.j < extra ? 1 : 0);
+        t.p0 = 128 * (t.j * base + min(t.j, extra));
+        t.h0 = t.p0 / Wp;
+        t.c0 = t.p0 - t.h0 * Wp;
+        return true;
+    };
+    // consumer side of the tile queue (one elected lane per consumer warp arrives on q_empty)
+    int qs = 0;
+    uint32_t qph = 0;
+    auto next_tile = [&](bool whole_warp) -> int {
+        mb_wait(&q_full[qs], qph);
+        const int i = tile_q[qs];
+        if (whole_warp) __syncwarp();
+        if (lane == 0) mb_arrive(&q_empty[qs]);
+        if (++qs == kG2Queue) {
+            qs = 0;
+            qph ^= 1;
+        }
+        return i;
     };
 
     if (warp == 0) {
-        // ============================== TMA producer ==============================
+        // ============================== scheduler + TMA producer ==============================
         if (lane == 0) {
             const CUtensorMap* maps[kG2Classes] = {&ta0, &ta1, &ta2, &ta3};
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
-            for (int i = blockIdx.x; i < p.n_tiles; i += gridDim.x) {
-                int r, j, e, kc;
-                if (!tile_at(i, r, j, e, kc)) continue;
-                const int k = p.ksize[kc], pad = (k - 1) >> 1, taps = k * k;
-                const int h0 = p.strip_h0[kc][j];
-                const int wrow = p.wrow[e];
-                for (int c = 0; c < p.upt; ++c) {
-                    mb_wait(&a_empty[as], aph ^ 1);
-                    mb_expect_tx(&a_full[as], (uint32_t)p.box_bytes[kc]);
-                    tma_load_4d(a_buf + (size_t)as * p.a_stage_bytes, maps[kc], &a_full[as], c * KC, -pad, h0 - pad, r);
-                    if (++as == Cfg::A_STAGES) {
-                        as = 0;
-                        aph ^= 1;
-                    }
-                    for (int t = 0; t < taps; t += Cfg::TPS) {
-                        mb_wait(&b_empty[bs], bph ^ 1);
-                        mb_expect_tx(&b_full[bs], (uint32_t)Cfg::B_STAGE);
-                        // TPS consecutive taps are TPS*N consecutive rows of the tap-major weight block: one box
-                        // (a trailing odd tap drags in N rows of the next block / OOB zeros; they are not used)
-                        tma_load_2d(b_buf + (size_t)bs * Cfg::B_STAGE, &tmap_b, &b_full[bs], c * KC, wrow + t * N);
-                        if (++bs == Cfg::B_STAGES) {
-                            bs = 0;
-                            bph ^= 1;
+            // The producer walks the sequence of A items = (tile, channel chunk).  The halo box of item m+1 is
+            // requested while the weights of item m are still streaming (after B_STAGES weight stages of item m, when
+            // item m-1 has provably drained and its halo buffer is free), so the MMAs never wait for it.
+            G2Tile cur, nxt;
+            int cur_c = 0, nxt_c = 0;
+            bool more = true;                       // the scheduler still has tiles
+            auto advance = [&](const G2Tile& from, int from_c, bool first, G2Tile& to, int& to_c) -> bool {
+                if (!first && from_c + 1 < p.upt) {
+                    to = from;
+                    to_c = from_c + 1;
+                    return true;
+                }
+                while (more) {
+                    int i = atomicAdd(p.sched, 1);
+                    if (i >= p.n_tiles) i = -1;
+                    const bool ok = i >= 0 && tile_at(i, to);
+                    // the other roles see valid tiles, the zero-fill tiles of unused tail rows and the end marker; the
+                    // empty tile slots of a kernel-size class with fewer tiles than smax are dropped here.  (The
+                    // producer may block on a full queue while weight stages of the current tile are outstanding, so a
+                    // run of non-compute entries between two compute tiles must stay below the queue depth: unused
+                    // rows come first in the reversed row order, before any tile is in flight.)
+                    if (ok || i < 0 || to.r >= n_rows || to.e < 0) {
+                        mb_wait(&q_empty[qs], qph ^ 1);
+                        tile_q[qs] = i;
+                        mb_arrive(&q_full[qs]);
+                        if (++qs == kG2Queue) {
+                            qs = 0;
+                            qph ^= 1;
                         }
                     }
+                    if (i < 0) {
+                        more = false;
+                        break;
+                    }
+                    if (ok) {
+                        to_c = 0;
+                        return true;
+                    }
                 }
+                return false;
+            };
+            auto load_a = [&](const G2Tile& t, int c) {
+                const int pad = (p.ksize[t.kc] - 1) >> 1;
+                mb_wait(&a_empty[as], aph ^ 1);
+                mb_expect_tx(&a_full[as], (uint32_t)p.box_bytes[t.kc]);
+                tma_load_4d(a_buf + (size_t)as * p.a_stage_bytes, maps[t.kc], &a_full[as], c * KC, -pad, t.h0 - pad, t.r);
+                if (++as == Cfg::A_STAGES) {
+                    as = 0;
+                    aph ^= 1;
+                }
+            };
+            bool have = advance(cur, 0, true, cur, cur_c);
+            if (have) load_a(cur, cur_c);
+            while (have) {
+                const int k = p.ksize[cur.kc], taps = k * k;
+                const int wrow = p.wrow[cur.e];
+                const int nst = (taps + Cfg::TPS - 1) / Cfg::TPS;
+                const int pre = nst - 1 < Cfg::B_STAGES ? nst - 1 : Cfg::B_STAGES;
+                bool have_next = false;
+                for (int s = 0; s < nst; ++s) {
+                    if (s == pre) {
+                        have_next = advance(cur, cur_c, false, nxt, nxt_c);
+                        if (have_next) load_a(nxt, nxt_c);
+                    }
+                    mb_wait(&b_empty[bs], bph ^ 1);
+                    mb_expect_tx(&b_full[bs], (uint32_t)Cfg::B_STAGE);
+                    // TPS consecutive taps are TPS*N consecutive rows of the tap-major weight block: one box
+                    // (a trailing odd tap drags in N rows of the next block / OOB zeros; they are not used)
+                    tma_load_2d(b_buf + (size_t)bs * Cfg::B_STAGE, &tmap_b, &b_full[bs], cur_c * KC, wrow + s * Cfg::TPS * N);
+                    if (++bs == Cfg::B_STAGES) {
+                        bs = 0;
+                        bph ^= 1;
+                    }
+                }
+                have = have_next;
+                cur = nxt;
+                cur_c = nxt_c;
             }
         }
     } else if (warp <= kG2Issuers) {
         // ============================== MMA issuers (warp w owns M-tile w-1) ==============================
-        if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
-                                       ((uint32_t)(128 >> 4) << 24);
-            const int mt = warp - 1;
-            int tcount = 0;
-            (void)tcount;
-            int as = 0, bs = 0, acc = 0;
-            uint32_t aph = 0, bph = 0, acc_ph = 0;
-            for (int i = blockIdx.x; i < p.n_tiles; i += gridDim.x) {
-                int r, j, e, kc;
-                if (!tile_at(i, r, j, e, kc)) continue;
-                const int k = p.ksize[kc], Wp = p.wp[kc], taps = k * k;
-                const int sh = p.strip_sh[kc][j];
-                const bool active = mt < ((sh * Wp + 127) >> 7);
-                if (mt == 0) G2T(0);
-                mb_wait(&t_empty[acc], acc_ph ^ 1);
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+        const int mt = warp - 1;
+        int tcount = 0;
+        (void)tcount;
+        int as = 0, bs = 0, acc = 0;
+        uint32_t aph = 0, bph = 0, acc_ph = 0;
+        for (; lane == 0;) {
+            const int i = next_tile(false);
+            if (i < 0) break;
+            G2Tile t;
+            if (!tile_at(i, t)) continue;
+            const int k = p.ksize[t.kc], Wp = p.wp[t.kc], taps = k * k;
+            const bool active = mt < t.mt_n;
+            if (mt == 0) G2T(0);
+            mb_wait(&t_empty[acc], acc_ph ^ 1);
+            tc_fence_after();
+            if (mt == 0) G2T(1);
+            const uint32_t d = tmem_base + (uint32_t)((acc * Cfg::MT_MAX + mt) * N);
+            for (int c = 0; c < p.upt; ++c) {
+                mb_wait(&a_full[as], aph);
                 tc_fence_after();
-                if (mt == 0) G2T(1);
-                const uint32_t d = tmem_base + (uint32_t)((acc * Cfg::MT_MAX + mt) * N);
-                for (int c = 0; c < p.upt; ++c) {
-                    mb_wait(&a_full[as], aph);
-                    tc_fence_after();
-                    if (mt == 0 && c == 0) G2T(2);
-                    // descriptor of this M-tile's first position; taps / k-slices only add to the 14-bit address field
-                    const uint64_t a_desc0 = umma_desc<KC>(s2u(a_buf + (size_t)as * p.a_stage_bytes) + (uint32_t)mt * 128u * Cfg::ROWB);
-                    for (int t0 = 0; t0 < taps; t0 += Cfg::TPS) {
-                        mb_wait(&b_full[bs], bph);
-                        if (active) {
-                            tc_fence_after();
-                            const uint64_t bd0 = umma_desc<KC>(s2u(b_buf + (size_t)bs * Cfg::B_STAGE));
+                if (mt == 0 && c == 0) G2T(2);
+                // descriptor of this M-tile's first position; taps / k-slices only add to the 14-bit address field
+                const uint64_t a_desc0 =
+                    umma_desc<KC>(s2u(a_buf + (size_t)as * p.a_stage_bytes) + (uint32_t)(t.c0 + mt * 128) * Cfg::ROWB);
+                for (int t0 = 0; t0 < taps; t0 += Cfg::TPS) {
+                    mb_wait(&b_full[bs], bph);
+                    if (active) {
+                        tc_fence_after();
+                        const uint64_t bd0 = umma_desc<KC>(s2u(b_buf + (size_t)bs * Cfg::B_STAGE));
 #pragma unroll
-                            for (int q = 0; q < Cfg::TPS; ++q) {
-                                const int t = t0 + q;
-                                if (t < taps) {
-                                    const int tr = t / k, ts = t - tr * k;
-                                    const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(tr * Wp + ts) * Cfg::ROWB) >> 4);
-                                    const uint64_t bd = bd0 + (uint64_t)((q * Cfg::B_TAP) >> 4);
+                        for (int q = 0; q < Cfg::TPS; ++q) {
+                            const int tp = t0 + q;
+                            if (tp < taps) {
+                                const int tr = tp / k, ts = tp - tr * k;
+                                const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(tr * Wp + ts) * Cfg::ROWB) >> 4);
+                                const uint64_t bd = bd0 + (uint64_t)((q * Cfg::B_TAP) >> 4);
 #pragma unroll
-                                    for (int kk = 0; kk < KC / 16; ++kk)
-                                        tc_mma(d, ad + 2 * kk, bd + 2 * kk, idesc, (c | t | kk) != 0);
-                                }
+                                for (int kk = 0; kk < KC / 16; ++kk)
+                                    tc_mma(d, ad + 2 * kk, bd + 2 * kk, idesc, (c | tp | kk) != 0);
                             }
-                            tc_commit(&b_empty[bs]);
-                        } else {
-                            mb_arrive(&b_empty[bs]);
                         }
-                        if (++bs == Cfg::B_STAGES) {
-                            bs = 0;
-                            bph ^= 1;
-                        }
+                        tc_commit(&b_empty[bs]);
+                    } else {
+                        mb_arrive(&b_empty[bs]);
                     }
-                    if (active) tc_commit(&a_empty[as]);
-                    else mb_arrive(&a_empty[as]);
-                    if (++as == Cfg::A_STAGES) {
-                        as = 0;
-                        aph ^= 1;
+                    if (++bs == Cfg::B_STAGES) {
+                        bs = 0;
+                        bph ^= 1;
                     }
                 }
-                if (active) tc_commit(&t_full[acc]);
-                else mb_arrive(&t_full[acc]);
-                if (mt == 0) G2T(3);
-                ++tcount;
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_ph ^= 1;
+                if (active) tc_commit(&a_empty[as]);
+                else mb_arrive(&a_empty[as]);
+                if (++as == Cfg::A_STAGES) {
+                    as = 0;
+                    aph ^= 1;
                 }
+            }
+            if (active) tc_commit(&t_full[acc]);
+            else mb_arrive(&t_full[acc]);
+            if (mt == 0) G2T(3);
+            ++tcount;
+            if (++acc == 2) {
+                acc = 0;
+                acc_ph ^= 1;
             }
         }
     } else {
-        // ============================== epilogue (4 warps) ==============================
+        // ============================== epilogue (4 warps): TMEM -> registers -> global ==============================
         const int quad = warp & 3;
         int acc = 0;
         int tcount = 0;
         (void)tcount;
         uint32_t acc_ph = 0;
-        for (int i = blockIdx.x; i < p.n_tiles; i += gridDim.x) {
-            int r, j, e, kc;
-            if (!tile_at(i, r, j, e, kc)) {
-                // strips of an unused tail row: zero-fill so downstream elementwise ops stay finite
-                if (r >= n_rows || e < 0) {
+        for (;;) {
+            const int i = next_tile(true);
+            if (i < 0) break;
+            G2Tile t;
+            if (!tile_at(i, t)) {
+                // tiles of an unused tail row: zero-fill so downstream elementwise ops stay finite
+                if (t.r >= n_rows || t.e < 0) {
                     const int rows_per = (p.H + p.smax - 1) / p.smax;
-                    const int hs = j * rows_per, he = min(p.H, hs + rows_per);
+                    const int hs = t.j * rows_per, he = min(p.H, hs + rows_per);
                     const long long n16 = (long long)(he - hs) * p.W * N / 8;
-                    int4* o = reinterpret_cast<int4*>(p.Y + ((size_t)r * p.H + hs) * p.W * N);
+                    int4* o = reinterpret_cast<int4*>(p.Y + ((size_t)t.r * p.H + hs) * p.W * N);
                     for (long long q = quad * 32 + lane; q < n16; q += 128) o[q] = make_int4(0, 0, 0, 0);
                 }
                 continue;
             }
-            const int Wp = p.wp[kc];
-            const int h0 = p.strip_h0[kc][j], sh = p.strip_sh[kc][j];
-            const int mt_n = (sh * Wp + 127) >> 7;
+            const int Wp = p.wp[t.kc];
             mb_wait(&t_full[acc], acc_ph);
             tc_fence_after();
             if (quad == 0 && lane == 0) G2T(4);
-            const float* sc = p.scale ? p.scale + (size_t)r * N : nullptr;
-            // Each thread owns one position's channel vector; writing it straight to global memory would touch 32
-            // cache lines per warp store.  Stage the warp's 32 x N tile in shared memory (16-byte chunks, XOR
-            // swizzled against bank conflicts) and write it out with consecutive lanes on consecutive chunks.
-            constexpr int RB = N * 2, CPR = RB / 16;                    // row bytes, 16-byte chunks per row
-            uint8_t* stg = stage_buf + (size_t)quad * 32 * RB;
-            int32_t* poff = stage_off + quad * 32;
-            const int my_swz = (RB % 128 == 0) ? (lane & 7) : ((lane >> 1) & 3);
-            for (int mt = 0; mt < mt_n; ++mt) {
-                const int q = mt * 128 + quad * 32 + lane;
-                const int hl = q / Wp, w = q - hl * Wp;
-                const bool valid = hl < sh && w < p.W;
-                poff[lane] = valid ? (int32_t)((((size_t)r * p.H + (size_t)(h0 + hl)) * p.W + w)) : -1;
-#pragma unroll
-                for (int c0 = 0; c0 < N; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * Cfg::MT_MAX + mt) * N + c0), v);
-                    uint32_t packed[16];
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        float a = __uint_as_float(v[2 * u]), b = __uint_as_float(v[2 * u + 1]);
-                        if (sc) {
-                            a *= sc[c0 + 2 * u];
-                            b *= sc[c0 + 2 * u + 1];
-                        }
-                        if (p.act == 1) {
-                            a = a / (1.f + __expf(-a)) * (1.f / 0.596f);
-                            b = b / (1.f + __expf(-b)) * (1.f / 0.596f);
-                        }
-                        __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
-                        packed[u] = *reinterpret_cast<uint32_t*>(&o);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = c0 / 8 + u;
-                        *reinterpret_cast<int4*>(stg + lane * RB + ((j ^ my_swz) << 4)) =
-                            make_int4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int it = 0; it < CPR; ++it) {
-                    const int f = it * 32 + lane;
-                    const int row = f / CPR, ch = f - row * CPR;
-                    const int pix = poff[row];
-                    if (pix >= 0) {
-                        const int swz = (RB % 128 == 0) ? (row & 7) : ((row >> 1) & 3);
-                        int4 val = *reinterpret_cast<const int4*>(stg + row * RB + ((ch ^ swz) << 4));
-                        const size_t go = (size_t)pix * N + ch * 8;
-                        if (p.res) {   // mp_sum folded: out = res_a * residual + res_b * value
-                            const int4 rr = *reinterpret_cast<const int4*>(p.res + go);
-                            const uint32_t* vi = reinterpret_cast<const uint32_t*>(&val);
-                            const uint32_t* ri = reinterpret_cast<const uint32_t*>(&rr);
-                            uint32_t oo[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float v0 = __uint_as_float(vi[u] << 16), v1 = __uint_as_float(vi[u] & 0xffff0000u);
-                                const float r0 = __uint_as_float(ri[u] << 16), r1 = __uint_as_float(ri[u] & 0xffff0000u);
-                                __nv_bfloat162 o = __floats2bfloat162_rn(p.res_a * r0 + p.res_b * v0, p.res_a * r1 + p.res_b * v1);
-                                oo[u] = *reinterpret_cast<uint32_t*>(&o);
-                            }
-                            val = make_int4(oo[0], oo[1], oo[2], oo[3]);
-                        }
-                        *reinterpret_cast<int4*>(p.Y + go) = val;
-                    }
-                }
-                __syncwarp();
+            // one compact, branch-free instantiation per (scale, activation, residual) combination: the fully unrolled
+            // generic body was ~2 100 instructions per M-tile and ran at instruction-fetch speed (12 k cycles per tile)
+            const int fl = (p.scale ? 1 : 0) | (p.act == 1 ? 2 : 0) | (p.res ? 4 : 0);
+            const int q0 = t.p0 + quad * 32 + lane;
+            const uint32_t tc0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * Cfg::MT_MAX * N);
+            switch (fl) {
+                case 0: g2_epilogue<N, false, false, false>(p, t, q0, tc0); break;
+                case 1: g2_epilogue<N, true, false, false>(p, t, q0, tc0); break;
+                case 2: g2_epilogue<N, false, true, false>(p, t, q0, tc0); break;
+                case 3: g2_epilogue<N, true, true, false>(p, t, q0, tc0); break;
+                case 4: g2_epilogue<N, false, false, true>(p, t, q0, tc0); break;
+                case 5: g2_epilogue<N, true, false, true>(p, t, q0, tc0); break;
+                case 6: g2_epilogue<N, false, true, true>(p, t, q0, tc0); break;
+                default: g2_epilogue<N, true, true, true>(p, t, q0, tc0); break;
             }
             tc_fence_before();
             __syncwarp();
@@ -347,13 +472,22 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
     }
+    if (threadIdx.x == 0) {
+        // the last CTA to finish re-arms the scheduler for the next launch on this stream
+        __threadfence();
+        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 template <int KC, int N>
 static int launch_gconv2(const CUtensorMap* ta, const CUtensorMap& tb, const GConv2Params& p, cudaStream_t st) {
     using Cfg = Conv2Cfg<KC, N>;
     auto kfn = gconv2_fwd_kernel<KC, N>;
-    const int smem = Cfg::A_STAGES * p.a_stage_bytes + Cfg::B_STAGES * Cfg::B_STAGE + 4 * 32 * N * 2 + 1024;
+    const int smem = Cfg::A_STAGES * p.a_stage_bytes + Cfg::B_STAGES * Cfg::B_STAGE + 1024;
     HDMOE_CHECK_ARG(smem <= 227 * 1024, "gconv2: tile does not fit shared memory (%d bytes)", smem);
     HDMOE_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
@@ -380,7 +514,8 @@ extern "C" int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_
     HDMOE_CHECK_ARG(Cout == 32 || Cout == 64 || Cout == 96 || Cout == 128, "gconv2_fwd: Cout must be 32, 64, 96 or 128");
     HDMOE_CHECK_ARG(Cin_pad >= 32 && Cin_pad % 32 == 0, "gconv2_fwd: Cin_pad must be a multiple of 32 (got %d)", Cin_pad);
     HDMOE_CHECK_ARG(H >= 1 && H <= 255 && W >= 1 && W <= 248, "gconv2_fwd: H <= 255, W <= 248");
-    HDMOE_CHECK_ARG((((uintptr_t)X | (uintptr_t)Wt | (uintptr_t)Y) & 15) == 0, "gconv2_fwd: 16-byte alignment required");
+    HDMOE_CHECK_ARG((((uintptr_t)X | (uintptr_t)Wt) & 15) == 0, "gconv2_fwd: 16-byte alignment required");
+    HDMOE_CHECK_ARG((((uintptr_t)Y | (uintptr_t)residual) & 31) == 0, "gconv2_fwd: Y / residual need 32-byte alignment");
     EncodeTiledFn enc = get_tensor_map_encoder();
     if (!enc) {
         set_error("gconv2_fwd: cuTensorMapEncodeTiled not available from the driver");
@@ -402,7 +537,7 @@ extern "C" int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_
     p.res_a = res_a;
     p.res_b = res_b;
     // kernel-size classes and their strip tables
-    int ncls = 0, cls_k[kG2Classes], cls_shmax[kG2Classes];
+    int ncls = 0, cls_k[kG2Classes];
     for (int e = 0; e < n_experts; ++e) {
         const int k = ksize_host[e];
         HDMOE_CHECK_ARG(k >= 1 && k <= 7 && (k & 1), "gconv2_fwd: odd kernel sizes 1..7");
@@ -417,48 +552,48 @@ extern "C" int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_
         p.kclass[e] = (uint8_t)c;
         p.wrow[e] = wrow_host[e];
     }
-    int smax = 0, a_rows_max = 0;
-    for (int c = 0; c < ncls; ++c) {
-        const int k = cls_k[c], Wp = W + k - 1;
-        // strip height: the candidate (1..mt_max M-tiles) that needs the fewest M-tiles for the whole image
-        int best_sh = 0, best_cost = 1 << 30, best_n = 0;
-        for (int mt = mt_max; mt >= 1; --mt) {
-            int sh = (mt * 128) / Wp;
-            if (sh > H) sh = H;
-            if (sh < 1) continue;
-            const int n = (H + sh - 1) / sh;
-            if (n > kG2MaxStrips) continue;
-            int cost = 0;
+    int smax = 0, box_bytes_max = 0;
+    int cls_box_rows[kG2Classes];
+    const int b_ring_bytes = 4 * (Cout <= 64 ? 2 : 1) * Cout * KC * 2;      // Conv2Cfg: B_STAGES * B_STAGE
+    // M-tiles per tile: as many as there are issuer warps, fewer only if two halo buffers would not fit shared memory
+    for (int mt_try = mt_max; mt_try >= 1; --mt_try) {
+        smax = 0;
+        box_bytes_max = 0;
+        for (int c = 0; c < ncls; ++c) {
+            const int k = cls_k[c], Wp = W + k - 1;
+            // M-tiles of 128 positions over the flattened padded image [0, H*Wp), split as evenly as possible into
+            // tiles of <= mt_try M-tiles (tiles need not start on an image row)
+            const int m_total = (H * Wp + 127) / 128;
+            const int n = (m_total + mt_try - 1) / mt_try;
+            const int base = m_total / n, extra = m_total % n;
+            // input rows one tile's TMA box must hold: the tile's positions plus the largest tap offset
+            // (k-1)*(Wp+1), counted from the start of the image row that contains the tile's first position
+            int box_rows = 0;
             for (int j = 0; j < n; ++j) {
-                const int s_ = (j == n - 1) ? H - sh * (n - 1) : sh;
-                cost += (s_ * Wp + 127) / 128;
+                const int m0 = j * base + (j < extra ? j : extra), mt_n = base + (j < extra ? 1 : 0);
+                const int c0 = (128 * m0) % Wp;
+                const int rows = (c0 + 128 * mt_n - 1 + (k - 1) * (Wp + 1)) / Wp + 1;
+                if (rows > box_rows) box_rows = rows;
             }
-            if (cost < best_cost) {
-                best_cost = cost;
-                best_sh = sh;
-                best_n = n;
-            }
+            HDMOE_CHECK_ARG(box_rows <= 256 && Wp <= 256, "gconv2_fwd: TMA box too large");
+            p.ksize[c] = k;
+            p.wp[c] = Wp;
+            p.ntile[c] = n;
+            p.mt_base[c] = base;
+            p.mt_extra[c] = extra;
+            cls_box_rows[c] = box_rows;
+            p.box_bytes[c] = box_rows * Wp * KC * 2;
+            if (n > smax) smax = n;
+            if (p.box_bytes[c] > box_bytes_max) box_bytes_max = p.box_bytes[c];
         }
-        HDMOE_CHECK_ARG(best_sh > 0, "gconv2_fwd: image %dx%d with kernel %d does not tile", H, W, k);
-        p.ksize[c] = k;
-        p.wp[c] = Wp;
-        p.nstrips[c] = (uint8_t)best_n;
-        for (int j = 0; j < best_n; ++j) {
-            p.strip_h0[c][j] = (uint8_t)(j * best_sh);
-            p.strip_sh[c][j] = (uint8_t)((j == best_n - 1) ? H - best_sh * (best_n - 1) : best_sh);
-        }
-        cls_shmax[c] = best_sh;
-        p.box_bytes[c] = (best_sh + k - 1) * Wp * KC * 2;
-        if (best_n > smax) smax = best_n;
-        const int a_rows = mt_max * 128 + (k - 1) * (Wp + 1);
-        const int box_rows = (best_sh + k - 1) * Wp;
-        if (a_rows > a_rows_max) a_rows_max = a_rows;
-        if (box_rows > a_rows_max) a_rows_max = box_rows;
-        HDMOE_CHECK_ARG(best_sh + k - 1 <= 256 && Wp <= 256, "gconv2_fwd: TMA box too large");
+        if (2 * (((box_bytes_max + 1023) / 1024) * 1024) + b_ring_bytes + 1024 <= 227 * 1024) break;
     }
     p.smax = smax;
     p.n_tiles = cap_rows * smax;
-    p.a_stage_bytes = ((a_rows_max * KC * 2 + 1023) / 1024) * 1024;
+    p.a_stage_bytes = ((box_bytes_max + 1023) / 1024) * 1024;
+    cudaStream_t st = (cudaStream_t)stream;
+    p.sched = sched_slot(st);
+    HDMOE_CHECK_ARG(p.sched != nullptr, "gconv2_fwd: more than %d distinct streams in use", kSchedSlots);
     CUtensorMap ta[kG2Classes], tb;
     const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     for (int c = 0; c < kG2Classes; ++c) {
@@ -466,7 +601,7 @@ extern "C" int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_
         const int k = cls_k[cc], Wp = W + k - 1;
         cuuint64_t dims[4] = {(cuuint64_t)Cin_pad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)cap_rows};
         cuuint64_t strides[3] = {(cuuint64_t)Cin_pad * 2, (cuuint64_t)W * Cin_pad * 2, (cuuint64_t)H * W * Cin_pad * 2};
-        cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)Wp, (cuuint32_t)(cls_shmax[cc] + k - 1), 1};
+        cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)Wp, (cuuint32_t)cls_box_rows[cc], 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&ta[c], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(X), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -489,7 +624,6 @@ extern "C" int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_
             return HDMOE_ERR_CUDA;
         }
     }
-    cudaStream_t st = (cudaStream_t)stream;
 #define GC2(KCV, NV) \
     if (KC == KCV && Cout == NV) return launch_gconv2<KCV, NV>(ta, tb, p, st);
     GC2(32, 32) GC2(32, 64) GC2(32, 96) GC2(32, 128) GC2(64, 32) GC2(64, 64) GC2(64, 96) GC2(64, 128)

@@ -13,11 +13,13 @@
 // and zero-filled, so padding positions contribute nothing; B = the zero-padded input window of the strip, ONE
 // box per channel chunk; tap (r, s) reads it at start + (r * Wp + s) rows.  One MMA consumes 16 positions.
 //
-// Work decomposition (static, no host knowledge of the routing): item = (chunk of kRowsPerItem consecutive
-// rows, tap group g).  Rows are expert-major, so an item sees at most a few expert changes; accumulators are
-// flushed (vector atomics into the fp32 tap-major gradient buffer) at each change and at the end: split-K over
-// row chunks.  Tap groups exist because all taps of a group keep their [Cout x Cin_chunk] accumulators in the
-// 512 TMEM columns at once.
+// Work decomposition (no host knowledge of the routing): item = (chunk of rows_per_item consecutive rows, tap
+// group g).  Rows are expert-major, so an item sees at most a few expert changes; accumulators are flushed (vector
+// atomics into the fp32 tap-major gradient buffer) at each change and at the end: split-K over row chunks.  Tap
+// groups exist because all taps of a group keep their [Cout x Cin_chunk] accumulators in the 512 TMEM columns at
+// once.  Items are handed out dynamically, last rows (the large-kernel experts) first, from a self-resetting global
+// counter: a 5x5 item costs 1.5-2x a 3x3 item and tap groups beyond a small kernel's are empty, so the static
+// stride left CTAs with 4 032 MMAs next to an average of 2 440 (65 % imbalance at B = 256).
 //
 // Roles: warp 0 TMA producer, warps 1-3 MMA issuers (taps of the group are dealt round-robin; one thread
 // sustains only ~1 MMA / 100 cycles, tools/umma_rate.cu), warps 4-7 epilogue.
@@ -31,6 +33,7 @@ constexpr int kWgThreads = 32 * (1 + kWgIssuers + 4);
 constexpr int kWgClasses = 4;
 constexpr int kWgMaxE = HDMOE_MAX_EXPERTS;
 constexpr int kWgStages = 2;
+constexpr int kWgQueue = 8;            // item-id queue between the scheduler (producer lane) and the other roles
 
 struct WGradParams {
     int n_items, gmax, rows_per_item, cap_rows;
@@ -42,6 +45,7 @@ struct WGradParams {
     const int32_t* row_expert;
     const int32_t* n_rows_dev;
     float* dW;                         // fp32 [w_rows_total][cin_pad], tap-major blocks per expert (accumulated)
+    int32_t* sched;                    // [0] next item, [1] finished CTAs (self-resetting, core.cu)
     int32_t wrow[kWgMaxE];
     uint8_t kclass[kWgMaxE];
     int32_t ksize[kWgClasses], wp[kWgClasses], ngroups[kWgClasses], tg[kWgClasses];
@@ -71,7 +75,8 @@ gwgrad_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ C
     constexpr int ROWA = COUT * 2, ROWB_ = KC * 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full[kWgStages], empty[kWgStages], t_full, t_empty;
+    __shared__ __align__(8) uint64_t full[kWgStages], empty[kWgStages], t_full, t_empty, q_full[kWgQueue], q_empty[kWgQueue];
+    __shared__ int32_t item_q[kWgQueue];
     __shared__ uint32_t tmem_base_s;
     const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,6 +91,10 @@ gwgrad_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ C
         }
         mb_init(&t_full, kWgIssuers);
         mb_init(&t_empty, 4);
+        for (int q = 0; q < kWgQueue; ++q) {
+            mb_init(&q_full[q], 1);
+            mb_init(&q_empty[q], kWgIssuers + 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -103,7 +112,7 @@ gwgrad_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ C
     // Walk of one item, identical in every role.  Calls stage(r, e, kc, strip, chunk, first) for every pipeline
     // stage and flush(e, kc) whenever the accumulators must be written out.
     auto walk = [&](int item, auto&& stage_fn, auto&& flush_fn) {
-        const int g = item % p.gmax, rc = item / p.gmax;
+        const int g = item % p.gmax, rc = p.n_items / p.gmax - 1 - item / p.gmax;       // last row chunks first
         const int r0 = rc * p.rows_per_item, r1 = min(r0 + p.rows_per_item, n_rows);
         int cur_e = -1, cur_kc = 0;
         bool fresh = true;
@@ -127,14 +136,39 @@ gwgrad_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ C
         if (cur_e >= 0) flush_fn(cur_e, cur_kc, g);
     };
 
+    // item queue: the producer lane draws item ids from the global counter and publishes them (-1 = end)
+    int qs = 0;
+    uint32_t qph = 0;
+    auto next_item = [&](bool whole_warp) -> int {
+        mb_wait(&q_full[qs], qph);
+        const int i = item_q[qs];
+        if (whole_warp) __syncwarp();
+        if (lane == 0) mb_arrive(&q_empty[qs]);
+        if (++qs == kWgQueue) {
+            qs = 0;
+            qph ^= 1;
+        }
+        return i;
+    };
+
     if (warp == 0) {
-        // ============================== TMA producer ==============================
+        // ============================== scheduler + TMA producer ==============================
         if (lane == 0) {
             const CUtensorMap* ma[kWgClasses] = {&ta0, &ta1, &ta2, &ta3};
             const CUtensorMap* mb[kWgClasses] = {&tb0, &tb1, &tb2, &tb3};
             int s = 0;
             uint32_t ph = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            for (;;) {
+                int item = atomicAdd(p.sched, 1);
+                if (item >= p.n_items) item = -1;
+                mb_wait(&q_empty[qs], qph ^ 1);
+                item_q[qs] = item;
+                mb_arrive(&q_full[qs]);
+                if (++qs == kWgQueue) {
+                    qs = 0;
+                    qph ^= 1;
+                }
+                if (item < 0) break;
                 walk(item,
                      [&](int r, int e, int kc, int g, int st, int c, bool) {
                          const int pad = (p.ksize[kc] - 1) >> 1;
@@ -160,7 +194,9 @@ gwgrad_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ C
             const int me = warp - 1;
             int s = 0;
             uint32_t ph = 0, tph = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            for (;;) {
+                const int item = next_item(false);
+                if (item < 0) break;
                 walk(item,
                      [&](int r, int e, int kc, int g, int st, int c, bool first) {
                          const int k = p.ksize[kc], Wp = p.wp[kc];
@@ -198,7 +234,9 @@ gwgrad_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ C
         // ============================== epilogue: TMEM -> vector atomics ==============================
         const int quad = warp & 3;
         uint32_t tph = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (;;) {
+            const int item = next_item(true);
+            if (item < 0) break;
             walk(item, [&](int, int, int, int, int, int, bool) {},
                  [&](int e, int kc, int g) {
                      const int k = p.ksize[kc];
@@ -234,6 +272,15 @@ gwgrad_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ C
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+    if (threadIdx.x == 0) {
+        // the last CTA to finish re-arms the scheduler for the next launch on this stream
+        __threadfence();
+        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
+        }
     }
 }
 
@@ -330,8 +377,9 @@ extern "C" int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int c
     p.a_stage_bytes = ((a_max + 1023) / 1024) * 1024;
     p.b_stage_bytes = ((b_max + 1023) / 1024) * 1024;
     p.gmax = gmax;
-    // rows per item: ~2 items per SM
-    int rpi = (cap_rows * gmax + 2 * kNumSMs - 1) / (2 * kNumSMs);
+    // rows per item: >= 8 items per SM for the dynamic scheduler (an item ends with one flush of the group's
+    // accumulators, ~2 k cycles during which the MMAs of the CTA wait, so items should not be smaller than needed)
+    int rpi = cap_rows * gmax / (8 * kNumSMs);
     if (rpi < 1) rpi = 1;
     p.rows_per_item = rpi;
     p.n_items = ((cap_rows + rpi - 1) / rpi) * gmax;
@@ -369,6 +417,8 @@ extern "C" int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int c
     }
     (void)w_rows_total;
     cudaStream_t st = (cudaStream_t)stream;
+    p.sched = sched_slot(st);
+    HDMOE_CHECK_ARG(p.sched != nullptr, "gconv_wgrad: more than %d distinct streams in use", kSchedSlots);
     if (Cout == 64 && KC == 64) return launch_wgrad<64, 64>(ta, tb, p, st);
     if (Cout == 64 && KC == 32) return launch_wgrad<64, 32>(ta, tb, p, st);
     if (Cout == 32 && KC == 64) return launch_wgrad<32, 64>(ta, tb, p, st);

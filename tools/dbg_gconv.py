@@ -87,6 +87,10 @@ for args in [
     dict(R=4, H=32, W=32, Cin=32, Cout=32, ks=[3, 5], counts=[1, 3], res=True),
     dict(R=3, H=64, W=64, Cin=32, Cout=128, ks=[3], counts=[3]),
     dict(R=300, H=32, W=32, Cin=64, Cout=64, ks=[3, 3, 5, 5], counts=[40, 60, 90, 100]),
+    dict(R=3, H=64, W=64, Cin=64, Cout=64, ks=[5, 3], counts=[2, 1], scale=True, res=True),
+    dict(R=5, H=20, W=12, Cin=32, Cout=96, ks=[7, 1, 3], counts=[2, 1, 2], act=1),
+    dict(R=4, H=9, W=40, Cin=64, Cout=128, ks=[5, 3], counts=[1, 2], res=True),
+    dict(R=300, H=16, W=16, Cin=64, Cout=64, ks=[3, 3, 5, 5], counts=[40, 60, 90, 100], scale=True, act=1, res=True),
 ]:
     if run(**args) > 0.02:
         bad += 1

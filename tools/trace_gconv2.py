@@ -1,5 +1,6 @@
 import ctypes as C, sys, torch, numpy as np
-lib = C.CDLL("tools/libg2trace.so")
+import os
+lib = C.CDLL(os.environ.get("G2LIB", "tools/libg2trace.so"))
 dev = "cuda"
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 counts, ks = [36, 48, 75, 97], [3, 3, 5, 5]
@@ -21,26 +22,30 @@ for _ in range(3):
     rc = fn(p(x), p(wt), p(y), R, H, H, Cin, Cout, tot, p(re_d), p(nr_d), 4, ks_h, wr_h, None, 0, None, 0.0, 0.0, None)
     assert rc == 0
     torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ev[0].record()
+for _ in range(10):
+    fn(p(x), p(wt), p(y), R, H, H, Cin, Cout, tot, p(re_d), p(nr_d), 4, ks_h, wr_h, None, 0, None, 0.0, 0.0, None)
+ev[1].record(); torch.cuda.synchronize()
+print("lib", os.environ.get("G2LIB", "default"), "H", H, "us per launch (back-to-back, warm L2): %.1f" % (ev[0].elapsed_time(ev[1]) * 100))
 buf = (C.c_longlong * (148 * 64))()
 lib.hdmoe_g2_trace_read.argtypes = [C.c_void_p]
 lib.hdmoe_g2_trace_read(buf)
 a = np.array(buf[:], dtype=np.int64).reshape(148, 8, 8)
-for b in (0, 1, 70, 147):
+for b in (0, 147):
     print("CTA", b)
     t00 = a[b, 0, 0]
     for t in range(8):
         s = a[b, t, :6]
         if s[3] == 0: break
         print(f"  tile {t}: start +{s[0]-t00:7d}  wait_acc {s[1]-s[0]:6d}  wait_A {s[2]-s[1]:6d}  mma_issue {s[3]-s[2]:7d}  | mma_done-issue_end {s[4]-s[3]:7d}  epilogue {s[5]-s[4]:6d}")
-ends = []
-starts = []
-for b in range(148):
-    ts = [a[b, t, 5] for t in range(8) if a[b, t, 5] > 0]
-    if ts:
-        ends.append(max(ts)); starts.append(a[b, 0, 0])
-ends = np.array(ends); starts = np.array(starts)
-g0 = starts.min()
-print("first tile start spread:", (starts - g0).min(), (starts - g0).max())
-e = ends - g0
-print("CTA end times: min %d  median %d  max %d   (tiles/CTA: %s)" % (e.min(), np.median(e), e.max(),
-      np.bincount([sum(1 for t in range(8) if a[b, t, 5] > 0) for b in range(148)]).tolist()))
+# SM clock from the cycle counter vs the nanosecond global timer, and the wall-clock span of the launch
+g_start = min(a[b, 0, 6] for b in range(148) if a[b, 0, 6] > 0)
+g_end = max(a[b, t, 7] for b in range(148) for t in range(8))
+print("launch span by globaltimer (first tile start -> last traced epilogue end): %.1f us" % ((g_end - g_start) / 1e3))
+for b in (0, 73, 147):
+    last = max(t for t in range(8) if a[b, t, 5] > 0)
+    cyc = a[b, last, 5] - a[b, 0, 0]; ns = a[b, last, 7] - a[b, 0, 6]
+    print(f"CTA {b}: {cyc} cycles in {ns} ns -> {cyc / ns:.3f} GHz; start offset {(a[b, 0, 6] - g_start) / 1e3:.1f} us, end offset {(a[b, last, 7] - g_start) / 1e3:.1f} us")
+ends_ns = sorted((max(a[b, t, 7] for t in range(8)) - g_start) / 1e3 for b in range(148))
+print("CTA end times (us): min %.1f median %.1f max %.1f" % (ends_ns[0], ends_ns[74], ends_ns[-1]))
