@@ -52,6 +52,7 @@ PROTOTYPES = {
     "hdmoe_gconv_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
     "hdmoe_gconv2_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
     "hdmoe_gconv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p]),
+    "hdmoe_gconv_wgrad_v1": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p]),
     "hdmoe_nhwc_pixnorm_silu_fwd": (_i, [_p, _p, _p, _i64, _i, _p]),
     "hdmoe_nhwc_pixnorm_silu_bwd": (_i, [_p, _p, _p, _p, _i64, _i, _p]),
     "hdmoe_nhwc_gain_silu_fwd": (_i, [_p, _p, _p, _i64, _i64, _i, _p]),

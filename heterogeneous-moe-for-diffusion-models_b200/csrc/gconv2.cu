@@ -193,6 +193,11 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
         }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 32) {   // descriptor fetches overlap the barrier / TMEM / row-cache set-up
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&ta0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&ta1) : "memory");
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::A_STAGES; ++s) {
             mb_init(&a_full[s], 1);
@@ -271,6 +276,7 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
             G2Tile cur, nxt;
             int cur_c = 0, nxt_c = 0;
             bool more = true;                       // the scheduler still has tiles
+            bool first_draw = true;                 // tile blockIdx.x is this CTA's without asking (saves one L2 round trip)
             auto advance = [&](const G2Tile& from, int from_c, bool first, G2Tile& to, int& to_c) -> bool {
                 if (!first && from_c + 1 < p.upt) {
                     to = from;
@@ -278,7 +284,8 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
                     return true;
                 }
                 while (more) {
-                    int i = atomicAdd(p.sched, 1);
+                    int i = first_draw ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(p.sched, 1);
+                    first_draw = false;
                     if (i >= p.n_tiles) i = -1;
                     const bool ok = i >= 0 && tile_at(i, to);
                     // the other roles see valid tiles, the zero-fill tiles of unused tail rows and the end marker; the

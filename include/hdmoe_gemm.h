@@ -43,6 +43,10 @@ int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H
 int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int cap_rows, int H, int W, int Cin_pad, int Cout,
                       int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev, int n_experts,
                       const int32_t* ksize_host, const int32_t* wrow_host, void* stream);
+/* v1 of the same operation (one M = 64 MMA per tap, single accumulator set); kept for A/B measurement. */
+int hdmoe_gconv_wgrad_v1(const void* X, const void* dY, float* dW, int cap_rows, int H, int W, int Cin_pad, int Cout,
+                      int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev, int n_experts,
+                      const int32_t* ksize_host, const int32_t* wrow_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,11 @@ sys.path.insert(0, '.')
 import hdmoe_b200
 from hdmoe_b200 import _lib as L
 lib = L.lib()
+import os
+if os.environ.get('WGLIB'):
+    lib = C.CDLL(os.environ['WGLIB'])
+    lib.hdmoe_gconv_wgrad.restype = C.c_int
+    lib.hdmoe_gconv_wgrad.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 dev = "cuda"
 p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
 
@@ -23,7 +28,8 @@ def run(R, H, W, Cin, Cout, ks, counts, time_it=False):
     re_d = torch.tensor(row_e, dtype=torch.int32, device=dev); nr_d = torch.tensor([n_rows], dtype=torch.int32, device=dev)
     ks_h = (C.c_int32 * E)(*ks); wr_h = (C.c_int32 * E)(*wrow)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    call = lambda: L.check(lib.hdmoe_gconv_wgrad(p(xd), p(dyd), p(dW), R, H, W, Cin, Cout, tot, p(re_d), p(nr_d), E, ks_h, wr_h, st), "wgrad")
+    FN = lib.hdmoe_gconv_wgrad_v1 if os.environ.get('WGV1') else lib.hdmoe_gconv_wgrad
+    call = lambda: L.check(FN(p(xd), p(dyd), p(dW), R, H, W, Cin, Cout, tot, p(re_d), p(nr_d), E, ks_h, wr_h, st), "wgrad")
     call()
     torch.cuda.synchronize()
     got = dW.cpu()
@@ -50,6 +56,15 @@ def run(R, H, W, Cin, Cout, ks, counts, time_it=False):
         ms = a.elapsed_time(b) / 5
         fl = sum(2.0 * c * H * W * Cout * Cin * k * k for c, k in zip(counts, ks))
         msg += f"   {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s"
+        if os.environ.get('WGLIB'):
+            import numpy as np
+            buf = (C.c_longlong * (148 * 16))()
+            lib.hdmoe_wg_trace_read.argtypes = [C.c_void_p]
+            lib.hdmoe_wg_trace_read(buf)
+            a = np.array(buf[:], dtype=np.int64).reshape(148, 16)[:, :6]
+            names = ["wait_item", "decode", "wait_tma", "issue", "flush", "n_items"]
+            msg += "\n    issuer-0 cycles per CTA (mean / max): " + "  ".join(f"{n} {a[:, i].mean():.0f}/{a[:, i].max()}" for i, n in enumerate(names))
+            msg += f"\n    total {a[:, :5].sum(1).mean():.0f} / {a[:, :5].sum(1).max()}"
     print(msg, flush=True)
     return worst
 
@@ -64,6 +79,9 @@ for a in [dict(R=2, H=16, W=16, Cin=64, Cout=64, ks=[1], counts=[2]),
           dict(R=40, H=32, W=32, Cin=64, Cout=64, ks=[3, 3, 5, 5], counts=[5, 10, 12, 13]),
           dict(R=256, H=32, W=32, Cin=64, Cout=64, ks=[3, 3, 5, 5], counts=[36, 48, 75, 97], time_it=True),
           dict(R=256, H=16, W=16, Cin=64, Cout=64, ks=[3, 3, 5, 5], counts=[36, 48, 75, 97], time_it=True),
-          dict(R=256, H=32, W=32, Cin=32, Cout=32, ks=[3, 3, 5, 5], counts=[36, 48, 75, 97], time_it=True)]:
+          dict(R=256, H=32, W=32, Cin=32, Cout=32, ks=[3, 3, 5, 5], counts=[36, 48, 75, 97], time_it=True),
+          dict(R=256, H=16, W=16, Cin=128, Cout=64, ks=[3, 3, 5, 5], counts=[36, 48, 75, 97], time_it=True),
+          dict(R=256, H=32, W=32, Cin=96, Cout=32, ks=[3, 3, 5, 5], counts=[36, 48, 75, 97], time_it=True),
+          dict(R=7, H=24, W=20, Cin=32, Cout=64, ks=[7, 1, 3], counts=[3, 2, 2])]:
     if run(**a) > 0.02: bad += 1
 print("BAD" if bad else "ALL OK", bad)

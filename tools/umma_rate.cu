@@ -14,7 +14,7 @@ __device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
         if (spin > (1u << 26)) { printf("rate: wait timeout\n"); __trap(); }
     }
 }
-template <int N, int M = 128>
+template <int N, int M = 128, int MN = 0>
 __global__ void __launch_bounds__(128) rate_kernel(int issuers, int iters, int naccs, int same_acc_run, long long* out) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(128) rate_kernel(int issuers, int iters, int n
     const uint32_t tmem = tmem_s;
     long long t0 = 0, t1 = 0;
     if (warp < issuers && lane == 0) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (((uint32_t)M >> 4) << 24);
-        const uint64_t base = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (((uint32_t)M >> 4) << 24) | (MN ? ((1u << 15) | (1u << 16)) : 0u);
+        // K-major: LBO field 1 (unused), SBO = 1024 B; MN-major: LBO = MN (in 16-byte units: 8 = next 128-byte row), SBO = 1024 B
+        const uint64_t base = ((uint64_t)(MN ? (MN == 1 ? 0 : MN) : 1) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+        const int kstep = MN ? 128 : 2;     // descriptor units (16 B) per K = 16 slice
         const uint64_t ad0 = base | ((s2u(smem) & 0x3FFFF) >> 4);
         const uint64_t bd0 = base | ((s2u(smem + 32 * 1024) & 0x3FFFF) >> 4);
         t0 = clock64();
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(128) rate_kernel(int issuers, int iters, int n
             for (int kk = 0; kk < 4; ++kk) {
                 const int acc = same_acc_run ? a : (warp * naccs + ((it * 4 + kk) % naccs));
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(tmem + (uint32_t)(acc * N)), "l"(ad0 + 2 * kk), "l"(bd0 + 2 * kk), "r"(idesc), "r"(1u) : "memory");
+                             ::"r"(tmem + (uint32_t)(acc * N)), "l"(ad0 + kstep * kk), "l"(bd0 + kstep * kk), "r"(idesc), "r"(1u) : "memory");
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(&bar[warp])) : "memory");
@@ -60,21 +62,21 @@ __global__ void __launch_bounds__(128) rate_kernel(int issuers, int iters, int n
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
-template <int N, int M = 128>
+template <int N, int M = 128, int MN = 0>
 int run(int issuers, int naccs, int same) {
     long long* d;
     CK(cudaMalloc(&d, 4 * sizeof(long long)));
     CK(cudaMemset(d, 0, 4 * sizeof(long long)));
     const int iters = 2000, smem = 65 * 1024 + 1024;
-    CK(cudaFuncSetAttribute(rate_kernel<N, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    rate_kernel<N, M><<<1, 128, smem>>>(issuers, iters, naccs, same, d);
+    CK(cudaFuncSetAttribute(rate_kernel<N, M, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rate_kernel<N, M, MN><<<1, 128, smem>>>(issuers, iters, naccs, same, d);
     CK(cudaDeviceSynchronize());
     long long h[4];
     CK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
     long long mx = 0;
     for (int i = 0; i < issuers; ++i) mx = h[i] > mx ? h[i] : mx;
     const double per = (double)mx / (iters * 4.0 * issuers);
-    printf("M=%3d N=%3d issuers=%d accs/issuer=%d %s: %7.1f cycles per MMA (ideal %d) -> %.0f%% of tensor peak\n", M, N, issuers, naccs,
+    printf("%s M=%3d N=%3d issuers=%d accs/issuer=%d %s: %7.1f cycles per MMA (ideal %d) -> %.0f%% of tensor peak\n", MN ? (MN == 1 ? "MN-major      " : "MN-major LBO=r") : "K-major       ", M, N, issuers, naccs,
            same ? "4 k-slices per acc" : "rotating acc     ", per, N / 2, 100.0 * (N / 2) * (M / 128.0) / per);
     cudaFree(d);
     return 0;
@@ -89,6 +91,7 @@ int main() {
     run<128>(1, 1, 1); run<128>(2, 1, 1); run<128>(3, 1, 1);
     run<256>(1, 1, 1); run<256>(2, 1, 1);
     run<64, 64>(1, 1, 1); run<64, 64>(3, 1, 1); run<128, 64>(1, 1, 1); run<128, 64>(3, 1, 1); run<256, 64>(1, 1, 1); run<256, 64>(2, 1, 1);
+    run<64, 64, 1>(1, 1, 1); run<64, 64, 1>(3, 1, 1); run<64, 64, 1>(4, 1, 1); run<64, 128, 8>(2, 1, 1); run<64, 128, 8>(3, 1, 1); run<64, 128, 8>(4, 1, 1); run<32, 128, 4>(3, 1, 1); run<32, 64, 1>(3, 1, 1); run<128, 64, 1>(3, 1, 1); run<128, 128, 8>(3, 1, 1);
     run<160>(1, 1, 1); run<160>(2, 1, 1); run<160>(3, 1, 1); run<192>(1,1,1); run<192>(2,1,1);
     return 0;
 }
