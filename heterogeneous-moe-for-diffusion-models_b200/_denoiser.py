@@ -126,6 +126,15 @@ def _run_experts_on_rows(experts, plan, xr, tr, txr):
             holder[key] = runner
         return runner(plan, xr, tr, txr, training=experts[0].training).contiguous()
     if _SYNC_FREE[0] and all(isinstance(ex, mc.Vit_expert) for ex in experts):
+        from . import vit_fused
+        if vit_fused.fusable(experts, xr):
+            # fused DiffiT-block kernels: 4 launches forward / 4 backward for the blocks of all experts
+            holder = experts.__dict__ if isinstance(experts, nn.ModuleList) else experts[0].__dict__
+            runner = holder.get("_hdmoe_fused_vit")
+            if runner is None:
+                runner = vit_fused.FusedVitExperts(experts)
+                holder["_hdmoe_fused_vit"] = runner
+            return runner(plan, xr, tr, txr)
         # Sync-free (CUDA-graph-capturable) execution of the cheap ViT experts (5-13 MFLOP per sample):
         # every expert sees all rows with static shapes and its rows are selected on the device; the reference's
         # "only experts that received samples run" rule for the train-mode weight rewrite is kept by a device flag.

@@ -239,13 +239,17 @@ int hdmoe_attn_d4_tc_bwd(const float* q, const float* k, const float* v, const f
  *      [128x32], linear3 [32x128].  aux: expert e's block at a_off[e]: GN (w, b), norm1 (w, b), norm2 (w, b), final
  *      LayerNorm (w, b) [32 each], rel_pos_bias [8][S_e][S_e].  final_ln: also apply the final LayerNorm
  *      (Vit_expert.norm, :698).  w_off / a_off / tokens are HOST arrays of n_experts (<= 8) entries.
- *      bwd: recomputes the block from tok_in; d_w_part / d_aux_part are [n_slices][w_total] / [n_slices][aux_total]
- *      scratch (zeroed by the kernel); slice c accumulates expert c % n_experts; the caller sums the slices of each
- *      expert.  counts_off: device [n_experts + 1] exclusive row offsets of the expert-major rows.
  * ---------------------------------------------------------------------------------------------- */
 int hdmoe_vit_block_fwd(const float* tok_in, const float* time, const int32_t* row_expert, const float* w_hat,
                         const float* aux, const int64_t* w_off, const int64_t* a_off, const int32_t* tokens, int n_experts,
                         int64_t rows, int final_ln, float* tok_out, hdmoe_stream_t stream);
+/* backward of the same block: recomputes it from tok_in.  d_out [rows][64][32] -> d_tok [rows][64][32] and d_time
+ * [rows][64] (written); d_w / d_aux: fp32 buffers laid out like w_hat / aux, ZEROED BY THE CALLER, accumulated with
+ * atomics (the rows of one expert meet there; the summation order is not deterministic). */
+int hdmoe_vit_block_bwd(const float* tok_in, const float* time, const int32_t* row_expert, const float* w_hat,
+                        const float* aux, const int64_t* w_off, const int64_t* a_off, const int32_t* tokens, int n_experts,
+                        int64_t rows, int final_ln, const float* d_out, float* d_tok, float* d_time, float* d_w,
+                        float* d_aux, hdmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (9) Router trunk normalisation: GroupNorm(num_groups = 1, C) + ReLU [+ AdaptiveAvgPool2d((1,1))] of

@@ -73,3 +73,9 @@ for sid, lst in sorted(by.items(), key=lambda kv: kv[1][0][0]):
         cur[1] = max(cur[1], e[1]); cur[2] += e[1] - e[0]
     wins.append(cur)
     print("    windows: " + "  ".join(f"[{(a-t0)/1e3:.2f}-{(b-t0)/1e3:.2f} busy {c/1e3:.2f}]" for a, b, c in wins))
+print("\n--- totals by kernel name (device time inside the replay) ---")
+tot = collections.Counter(); cnt = collections.Counter()
+for e in evs: tot[e[3]] += e[1] - e[0]; cnt[e[3]] += 1
+T = sum(tot.values())
+for k, v in tot.most_common(45):
+    print(f"{v/1e3:8.3f} ms {100*v/T:5.1f}% n={cnt[k]:5d}  {k}")
