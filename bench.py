@@ -339,6 +339,12 @@ def run_ours(args):
         roof = roofline_gconv(device, peaks, flush)
         disp = dispatch_sweep(device, peaks, flush, full=args.full_sweep)
         samp = sampler_throughput(device) if not args.no_sampler else None
+        cfg_c = None
+        if not args.no_sampler and world == 1:
+            try:
+                cfg_c = config_c_throughput(device)
+            except Exception as exc:                  # noqa: BLE001
+                cfg_c = {"error": str(exc)[:200]}
         cpu = cpu_baseline_train(sample_batch=8, iters=3)
         line = {"metric": "denoiser train img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
@@ -356,7 +362,7 @@ def run_ours(args):
                         "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3), "last_loss": loss_host},
                 "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu, "peaks": peaks["src"],
-                "dispatch": disp, "sampler": samp}
+                "dispatch": disp, "sampler": samp, "config_c": cfg_c}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -430,10 +436,27 @@ def roofline_gconv(device, peaks, flush, iters=10):
     us = _time_us(lambda: ops.gconv_raw(x, w, Cout, tot, row_e, n_rows, ks, wrow), flush, iters)
     flops = sum(2.0 * c * H * H * Cout * Cin * k * k for c, k in zip(counts, ks))
     ach = flops / us / 1e6
-    return {"bound": "tensor", "kernel": "gconv_fwd_kernel<64,64> (256 rows 32x32, Cin=Cout=64, k=3,3,5,5 routed 36/48/75/97)",
+    # weight gradient of the same layer (gwgrad2_kernel): same flops
+    dy = torch.randn(R, H, H, Cout, device=device).to(torch.bfloat16)
+    dw = torch.zeros(tot, Cin, device=device)
+    us_w = _time_us(lambda: ops.gconv_wgrad_raw(x, dy, dw, row_e, n_rows, ks, wrow), flush, iters)
+    name = "gconv2_fwd_kernel<64,64>"
+    return {"bound": "tensor", "kernel": name + " (256 rows 32x32, Cin=Cout=64, k=3,3,5,5 routed 36/48/75/97)",
             "achieved": round(ach, 1), "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": round(ach / peaks["bf16"], 4),
-            "traffic": None, "us_per_launch": round(us, 1), "algorithmic_flops": flops,
-            "peak_basis": "burst (kernel timed alone), " + peaks["src"]}
+            "traffic": ncu_traffic(name), "us_per_launch": round(us, 1), "algorithmic_flops": flops,
+            "peak_basis": "burst (kernel timed alone), " + peaks["src"],
+            "wgrad": {"kernel": "gwgrad2_kernel<64,64> (same layer)", "us_per_launch": round(us_w, 1),
+                      "achieved": round(flops / us_w / 1e6, 1), "frac": round(flops / us_w / 1e6 / peaks["bf16"], 4),
+                      "traffic": ncu_traffic("gwgrad2_kernel<64,64>")}}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    kernel at this shape (profiles/ncu_traffic.json, written from the .ncu-rep by tools/ncu_summary.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel)
 
 
 def sampler_throughput(device, B=1024, steps=18):
@@ -457,6 +480,59 @@ def sampler_throughput(device, B=1024, steps=18):
     return {"metric": "EDM sample img/s", "value": round(B / (ms / 1e3), 1), "unit": "img/s", "batch": B, "nfe": smp.nfe,
             "ms": round(ms, 1), "finite": bool(torch.isfinite(out).all()),
             "execution": "one CUDA graph per denoiser evaluation, fused Heun kernels between"}
+
+
+def config_c_throughput(device, B=64, steps=5):
+    """BASELINE configs[2] on ONE GPU: model_config2 at 4x64x64 (11.2 M parameters), bf16 expert path, whole train step
+    (fwd + EDM_LOSS + bwd + clip + AdamW) captured in a CUDA graph, batch 64."""
+    import hdmoe_b200
+    from hdmoe_b200.utils import EDM_LOSS
+    from hdmoe_b200.train_step import GraphedTrainStep
+    torch.manual_seed(0)
+    model = hdmoe_b200.model_config2.preconditioned_HDMOEM(**dict(FULL, IN_img_resolution=64))
+    gen = torch.Generator().manual_seed(100)
+    with torch.no_grad():
+        for p in model.parameters():
+            if float(p.abs().max()) == 0:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
+    model.to(device).train()
+    crit = EDM_LOSS(**LOSS)
+    params = list(model.parameters())
+    opt = torch.optim.AdamW(params, lr=5e-4, fused=True, capturable=True)
+    b = {k: v.to(device) for k, v in synth_batch(B, 64, 0, device).items()}
+
+    def step(b):
+        out = model(x=b["x"], sigma=b["sigma"], text_emb=b["text"], Unet_router_mask=b["um"], Vit_router_mask=b["vm"],
+                    zeta=2.0, transition_point=P_MEAN, softness=P_STD, return_log_var=True)
+        loss = crit(b["sigma"], b["x0"], b["sigma"], out)["loss"]
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    mode = "cuda_graph"
+    try:
+        g = GraphedTrainStep(step, b, warmup=3).capture()
+        run = lambda: g(None)
+    except Exception as exc:                          # noqa: BLE001
+        mode = "eager (graph capture failed: %s)" % str(exc)[:80]
+        run = lambda: step(b)
+        for _ in range(3):
+            run()
+    run()
+    torch.cuda.synchronize()
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = run()
+    c.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(c) / steps
+    del model, opt
+    return {"metric": "denoiser train img/s", "workload": "model_config2 4x64x64 train step, batch %d, 1 GPU" % B,
+            "value": round(B / (ms / 1e3), 1), "unit": "img/s", "ms_per_step": round(ms, 2), "execution": mode,
+            "finite": bool(torch.isfinite(loss).all())}
 
 
 # ---------------------------------------------------------------------------------------------------------

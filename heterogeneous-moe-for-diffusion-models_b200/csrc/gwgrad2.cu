@@ -327,7 +327,7 @@ extern "C" int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int c
     HDMOE_CHECK_ARG(n_experts >= 1 && n_experts <= kW2MaxE, "gconv_wgrad: 1 <= n_experts <= %d", kW2MaxE);
     HDMOE_CHECK_ARG(Cout == 32 || Cout == 64, "gconv_wgrad: Cout must be 32 or 64 (got %d)", Cout);
     HDMOE_CHECK_ARG(Cin_pad >= 32 && Cin_pad % 32 == 0 && Cin_pad <= 256, "gconv_wgrad: Cin_pad in 32..256, multiple of 32");
-    HDMOE_CHECK_ARG(H % 8 == 0 && W % 2 == 0 && H <= 248 && W <= 240, "gconv_wgrad: need H %% 8 == 0 and even W");
+    HDMOE_CHECK_ARG(H % 4 == 0 && H <= 248 && W <= 232, "gconv_wgrad: need H %% 4 == 0, H <= 248, W <= 232");
     HDMOE_CHECK_ARG((((uintptr_t)X | (uintptr_t)dY | (uintptr_t)dW) & 15) == 0, "gconv_wgrad: 16-byte alignment required");
     EncodeTiledFn enc = get_tensor_map_encoder();
     if (!enc) {
@@ -362,11 +362,17 @@ extern "C" int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int c
         p.wrow[e] = wrow_host[e];
         if (k > kmax) kmax = k;
     }
-    // strip height: largest multiple of 8 dividing H whose two stages fit shared memory for the widest kernel
+    // strip height: largest candidate dividing H whose two stages fit shared memory for the widest kernel.  The padded
+    // row pitch Wp is rounded up so that a strip is a whole number of 16-position MMA slices; the surplus columns are
+    // out of bounds for both boxes and zero-filled by TMA like the k-1 halo columns.
+    auto pitch = [&](int k, int sh) {
+        const int m = sh % 16 == 0 ? 1 : (sh % 8 == 0 ? 2 : 4);
+        return ((W + k - 1 + m - 1) / m) * m;
+    };
     int SH = 0;
-    for (int cand : {32, 16, 8}) {
+    for (int cand : {32, 16, 8, 4}) {
         if (H % cand) continue;
-        const int Wp = W + kmax - 1;
+        const int Wp = pitch(kmax, cand);
         const long long a = kW2Lead + (long long)cand * Wp * Cout * 2;
         const long long b = ((long long)(cand + kmax - 1) * Wp + (kmax - 1) + 16) * KC * 2;
         if (kW2Stages * (((a + 1023) / 1024 + (b + 1023) / 1024) * 1024) + 1024 <= 220 * 1024) {
@@ -381,8 +387,8 @@ extern "C" int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int c
     p.upg = kW2BufCols / Cin_pad;
     int gmax = 1, a_max = 0, b_max = 0;
     for (int c = 0; c < ncls; ++c) {
-        const int k = cls_k[c], Wp = W + k - 1;
-        HDMOE_CHECK_ARG((SH * Wp) % 16 == 0, "gconv_wgrad: strip of %d rows x %d padded columns is not a multiple of 16", SH, Wp);
+        const int k = cls_k[c], Wp = pitch(k, SH);
+        HDMOE_CHECK_ARG((SH * Wp) % 16 == 0 && Wp <= 256, "gconv_wgrad: strip of %d rows x %d padded columns is not a multiple of 16", SH, Wp);
         const int upr = (k + TPM - 1) / TPM;                    // units per kernel row
         const int nunits = k * upr;
         const int ng = (nunits + p.upg - 1) / p.upg;
@@ -415,7 +421,7 @@ extern "C" int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int c
     const CUtensorMapSwizzle swb = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     for (int c = 0; c < kW2Classes; ++c) {
         const int cc = c < ncls ? c : 0;
-        const int k = cls_k[cc], Wp = W + k - 1;
+        const int k = cls_k[cc], Wp = pitch(k, SH);
         cuuint32_t es[4] = {1, 1, 1, 1};
         {
             cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)cap_rows};

@@ -284,6 +284,8 @@ class GroupedUnetExperts:
         if self._wg_pending:
             torch.cuda.current_stream().wait_stream(self._wg_stream)
             self._wg_pending = False
+        from . import prepared
+        prepared.unalias_grads(self._params(), self.grad_flat)
         for buf, g in ((self.g_noise, g_noise), (self.g_text, g_text), (self.g_emb, g_emb)):
             if g is None:
                 buf.zero_()
@@ -301,7 +303,7 @@ class GroupedUnetExperts:
         self._wpb.run_uploaded()
         for e in range(self.E):
             self._gain_views[e].copy_(self.gain_grads[e])
-        return views
+        return prepared.deliver_grads(self._params(), views)
 
     # ------------------------------------------------------------------------------------------ wgrad
     def weight_grad(self, layer: _ConvLayer, x, dy):

@@ -15,6 +15,40 @@ from . import ops
 
 _REG: Dict[int, Tuple[torch.Tensor, float]] = {}
 
+# Gradient hand-off without AccumulateGrad's clone.  The weight gradients of a group are views of ONE persistent
+# buffer; returned from backward() they are cloned one by one (445 device-to-device copies per train step, ~1 ms at the
+# end of the backward).  With direct hand-off a parameter whose .grad is None receives the view itself and backward()
+# returns None for it; a parameter that already holds a gradient takes the normal autograd route.  Parameter hooks do
+# not fire for handed-off gradients (none are used on this path); keep zero_grad(set_to_none=True), the default.
+_DIRECT_GRADS = [True]
+
+
+def set_direct_grads(enabled: bool) -> None:
+    _DIRECT_GRADS[0] = bool(enabled)
+
+
+def unalias_grads(params: Sequence[torch.Tensor], buf: torch.Tensor) -> None:
+    """Before `buf` is overwritten: a .grad left over from an earlier backward that still aliases it is cloned
+    (gradient accumulation across backward passes keeps its meaning)."""
+    lo, hi = buf.data_ptr(), buf.data_ptr() + buf.numel() * buf.element_size()
+    for p_ in params:
+        g = p_.grad
+        if g is not None and lo <= g.data_ptr() < hi:
+            p_.grad = g.clone()
+
+
+def deliver_grads(params: Sequence[torch.Tensor], views: Sequence[torch.Tensor]) -> List[Optional[torch.Tensor]]:
+    if not _DIRECT_GRADS[0] or torch.is_grad_enabled():
+        return list(views)
+    out = []
+    for p_, v in zip(params, views):
+        if p_.grad is None and p_.requires_grad and p_.is_leaf:
+            p_.grad = v
+            out.append(None)
+        else:
+            out.append(v)
+    return out
+
 
 def lookup(module, gain) -> Optional[torch.Tensor]:
     ent = _REG.get(id(module))
@@ -84,6 +118,7 @@ class PreparedGroup:
         self._wp.run_uploaded(force=training)
 
     def _run_bwd(self, grads):
+        unalias_grads([m.weights for m in self.mods], self.dw_flat)
         dsts, srcs = [], []
         for v, g in zip(self.g_views, grads):
             if g is None:
@@ -103,7 +138,7 @@ class PreparedGroup:
             self._wpb.upload()
             self._sigb = sig
         self._wpb.run_uploaded()
-        return self.dw_views
+        return deliver_grads([m.weights for m in self.mods], self.dw_views)
 
     class _Ctx:
         def __init__(self, group, tensors):

@@ -133,3 +133,26 @@ def test_host_producers_match_reference():
     smp = EDM_Sampler(None, None, num_solve_steps=18)
     assert torch.equal(smp.t_steps()[:-1], g["sampler.t_steps18"])
     assert abs(float(EDM_LOSS.load_balance(torch.full((16, 4), 0.25), 4)) - 1.0) < 1e-6
+
+
+def test_direct_gradient_handoff_keeps_accumulation_semantics():
+    """prepared.deliver_grads / unalias_grads (host logic of the clone-free gradient hand-off): a parameter without
+    .grad receives the persistent view itself; one that already holds a gradient goes through autograd; a .grad that
+    still aliases the persistent buffer is cloned before the buffer is overwritten."""
+    import torch
+    from hdmoe_b200 import prepared
+    buf = torch.zeros(6)
+    p1, p2 = torch.nn.Parameter(torch.ones(2, 2)), torch.nn.Parameter(torch.ones(2))
+    views = [buf[0:4].view(2, 2), buf[4:6]]
+    buf.copy_(torch.arange(6.0))
+    p2.grad = torch.full((2,), 10.0)
+    with torch.no_grad():
+        out = prepared.deliver_grads([p1, p2], views)
+    assert out[0] is None and p1.grad.data_ptr() == buf.data_ptr()          # handed off, no copy
+    assert out[1] is views[1] and float(p2.grad[0]) == 10.0                  # existing gradient: autograd adds
+    with torch.enable_grad():                                                # double backward: never hand off
+        assert prepared.deliver_grads([p1, p2], views) == views
+    prepared.unalias_grads([p1, p2], buf)                                    # next backward is about to overwrite buf
+    assert p1.grad.data_ptr() != buf.data_ptr() and torch.equal(p1.grad, torch.tensor([[0.0, 1.0], [2.0, 3.0]]))
+    buf.zero_()
+    assert float(p1.grad.sum()) == 6.0

@@ -718,3 +718,118 @@ def test_gn1_relu_matches_torch(C, pool):
     assert rel_l2(out, ref.detach()) < 1e-5
     assert rel_l2(x.grad, xr.grad) < 2e-5
     assert rel_l2(gamma.grad, gr.grad) < 2e-5 and rel_l2(beta.grad, br.grad) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ fused ViT experts
+@pytest.mark.parametrize("train", [False, True])
+def test_fused_vit_block_kernels_match_composite_path(train):
+    """vit_fused.py / csrc/vit_block.cu (4 + 4 launches for the DiffiT blocks of all ViT experts of a layer) against the
+    composite torch path through one MoE layer: output, input gradients, every parameter gradient, and the
+    train-mode weight rewrite.  fp32 on both sides: rel-L2 <= 2e-4 (atomics change the summation order)."""
+    import hdmoe_b200
+    from hdmoe_b200 import model_components as mc, _denoiser as D, vit_fused
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    E, patches = 4, [4, 8, 8, 16]
+
+    def make():
+        torch.manual_seed(1)
+        ex = torch.nn.ModuleList([mc.Vit_expert(num_heads=8, num_groups=4, in_channels=32, seq_ln=(32 // p) ** 2,
+                                                emb_dim=32, num_blocks=4, patch_size=p, time_dim=64, text_dim=768)
+                                  for p in patches]).cuda()
+        with torch.no_grad():
+            for n, p in ex.named_parameters():
+                if "rel_pos_bias" in n or "pos_emb" in n or n.endswith("bias"):
+                    p.copy_(torch.randn_like(p) * 0.3)
+                elif n.endswith("weight") and p.ndim == 1:
+                    p.copy_(1 + 0.2 * torch.randn_like(p))
+        return ex
+
+    B = 37
+    gen = torch.Generator().manual_seed(5)
+    x0 = torch.randn(B, 32, 32, 32, generator=gen).cuda()
+    t0 = torch.randn(B, 64, generator=gen).cuda()
+    tx0 = torch.randn(B, 77, 768, generator=gen).cuda()
+    idx = torch.randint(0, E - 1, (B,), generator=gen)            # expert 3 receives no rows (weight rewrite gated off)
+    wr = torch.zeros(B, E).scatter_(1, idx[:, None], 1.0).cuda()
+    gy = torch.randn(B, 32, 32, 32, generator=gen).cuda()
+    res = {}
+    try:
+        for fused in (False, True):
+            vit_fused.set_fused_vit(fused)
+            ex = make()
+            ex.train(train)
+            x, t, tx = (v.clone().requires_grad_(True) for v in (x0, t0, tx0))
+            out = D.router_to_unet_experts(x, ex, wr, t, tx, top_k=1)
+            out.backward(gy)
+            torch.cuda.synchronize()
+            res[fused] = dict(out=out.detach(), dx=x.grad, dt=t.grad, dtx=tx.grad,
+                              **{"g." + n: (None if p.grad is None else p.grad.clone()) for n, p in ex.named_parameters()},
+                              **{"w." + n: p.detach().clone() for n, p in ex.named_parameters() if n.endswith("weights")})
+    finally:
+        vit_fused.set_fused_vit(True)
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert float(res[True]["out"].abs().max()) > 0
+    for k, a in res[False].items():
+        b = res[True][k]
+        assert (a is None) == (b is None), k
+        if a is None:
+            continue
+        if "k_time" in k and k.startswith("g."):
+            # adding one vector to every key leaves the softmax unchanged: the true gradient is 0, both sides hold noise
+            assert float(b.abs().max()) < 1e-3 * max(1.0, float(res[False]["g." + k[2:].replace("k_time", "q_time")].abs().max()))
+            continue
+        den = float(a.norm())
+        err = float((a - b).norm()) / den if den > 0 else float(b.norm())
+        assert err < 2e-4, (k, err)
+
+
+# ------------------------------------------------------------------------------------------------ config C (64x64)
+def test_config2_64x64_train_step_bf16_grouped_vs_fp32():
+    """BASELINE configs[2]: model_config2 at 4x64x64.  One train step through the bf16 grouped tcgen05 expert path
+    (gconv2 forward / data gradient, gwgrad2 weight gradient at 64x64 and 32x32) against the fp32 per-expert path:
+    loss, denoised output (rel-L2 <= 1e-2, the bf16 bar of north_star) and the all-parameter gradient."""
+    import hdmoe_b200
+    from hdmoe_b200.utils import EDM_LOSS, MaskGenerator, sample_sigma_hybrid
+    full = dict(FULL, IN_img_resolution=64)
+    torch.manual_seed(0)
+    model = hdmoe_b200.model_config2.preconditioned_HDMOEM(**full)
+    gen = torch.Generator().manual_seed(100)
+    with torch.no_grad():
+        for p in model.parameters():
+            if float(p.abs().max()) == 0:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
+    model.cuda().train()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if hasattr(mod, "dropout") and not isinstance(mod, torch.nn.Dropout):
+            mod.dropout = 0
+    B = 6
+    x0, sigma, x, text = _full_inputs(B, 64)
+    ones = torch.ones(B, 4).cuda()
+    noise = {"vit": torch.randn(B, 4, generator=gen).cuda(), "unet": torch.randn(B, 4, generator=gen).cuda()}
+    crit = EDM_LOSS(num_experts=4, sigma_data=0.5, Unet_bal=0.05, vit_bal=0.1, z_bal=0.005, prior_bal=0.0)
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    res = {}
+    try:
+        for mode, dt, grouped in (("bf16", torch.bfloat16, True), ("fp32", torch.float32, False)):
+            hdmoe_b200.set_expert_dtype(dt)
+            hdmoe_b200.set_grouped_experts(grouped)
+            model.load_state_dict(state0)
+            model.zero_grad(set_to_none=True)
+            out = model(x=x.cuda(), sigma=sigma.cuda(), text_emb=text.cuda(), Unet_router_mask=ones, Vit_router_mask=ones,
+                        zeta=0.5, transition_point=-1.2, softness=1.6, return_log_var=True, noise=noise)
+            loss = crit(sigma.cuda(), x0.cuda(), sigma.cuda(), out)["loss"]
+            loss.backward()
+            res[mode] = dict(out=out["denoised"].detach().float().cpu(), loss=float(loss),
+                             g={n: p.grad.detach().float().cpu() for n, p in model.named_parameters() if p.grad is not None})
+    finally:
+        hdmoe_b200.set_expert_dtype(torch.float32)
+        hdmoe_b200.set_grouped_experts(True)
+    assert abs(res["bf16"]["loss"] - res["fp32"]["loss"]) < 1e-2 * max(1.0, abs(res["fp32"]["loss"]))
+    assert rel_l2(res["bf16"]["out"], res["fp32"]["out"]) < TOLBF
+    assert set(res["bf16"]["g"]) == set(res["fp32"]["g"])
+    num = sum(float(((res["bf16"]["g"][n] - g) ** 2).sum()) for n, g in res["fp32"]["g"].items())
+    den = sum(float((g ** 2).sum()) for g in res["fp32"]["g"].values())
+    assert (num / den) ** 0.5 < 5e-2

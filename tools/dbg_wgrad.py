@@ -82,6 +82,9 @@ for a in [dict(R=2, H=16, W=16, Cin=64, Cout=64, ks=[1], counts=[2]),
           dict(R=256, H=32, W=32, Cin=32, Cout=32, ks=[3, 3, 5, 5], counts=[36, 48, 75, 97], time_it=True),
           dict(R=256, H=16, W=16, Cin=128, Cout=64, ks=[3, 3, 5, 5], counts=[36, 48, 75, 97], time_it=True),
           dict(R=256, H=32, W=32, Cin=96, Cout=32, ks=[3, 3, 5, 5], counts=[36, 48, 75, 97], time_it=True),
-          dict(R=7, H=24, W=20, Cin=32, Cout=64, ks=[7, 1, 3], counts=[3, 2, 2])]:
+          dict(R=7, H=24, W=20, Cin=32, Cout=64, ks=[7, 1, 3], counts=[3, 2, 2]),
+          dict(R=3, H=64, W=64, Cin=64, Cout=32, ks=[5, 3], counts=[2, 1]),
+          dict(R=5, H=64, W=64, Cin=32, Cout=32, ks=[3, 5], counts=[2, 3]),
+          dict(R=3, H=12, W=10, Cin=32, Cout=32, ks=[3], counts=[3])]:
     if run(**a) > 0.02: bad += 1
 print("BAD" if bad else "ALL OK", bad)

@@ -77,7 +77,21 @@ def glue_case():
         nhwc.nhwc_to_rows(nhwc.rows_to_nhwc(rows, 64)[..., :32].contiguous())
     return run
 
-cases = [gconv_case(), attn_case(), gn_case(), dispatch_case(), router_case(), glue_case()]
+def vit_case():
+    from hdmoe_b200 import model_components as mc, _denoiser as D
+    hdmoe_b200.set_expert_dtype(torch.bfloat16)
+    ex = torch.nn.ModuleList([mc.Vit_expert(num_heads=8, num_groups=4, in_channels=32, seq_ln=(32 // p) ** 2, emb_dim=32, num_blocks=4,
+                                            patch_size=p, time_dim=64, text_dim=768) for p in (4, 8, 8, 16)]).to(dev).train()
+    B = 256
+    x = torch.randn(B, 32, 32, 32, device=dev, requires_grad=True); t = torch.randn(B, 64, device=dev); tx = torch.randn(B, 77, 768, device=dev)
+    idx = torch.tensor(sum(([e] * c for e, c in enumerate([36, 48, 75, 97])), []), device=dev)
+    wr = torch.zeros(B, 4, device=dev).scatter_(1, idx[:, None], 1.0)
+    gy = torch.randn(B, 32, 32, 32, device=dev)
+    def run():
+        D.router_to_unet_experts(x, ex, wr, t, tx, top_k=1).backward(gy)
+    return run
+
+cases = [gconv_case(), attn_case(), gn_case(), dispatch_case(), router_case(), glue_case(), vit_case()]
 for c in cases:
     c(); c()
 torch.cuda.synchronize()
