@@ -829,7 +829,10 @@ def test_config2_64x64_train_step_bf16_grouped_vs_fp32():
         hdmoe_b200.set_grouped_experts(True)
     assert abs(res["bf16"]["loss"] - res["fp32"]["loss"]) < 1e-2 * max(1.0, abs(res["fp32"]["loss"]))
     assert rel_l2(res["bf16"]["out"], res["fp32"]["out"]) < TOLBF
-    assert set(res["bf16"]["g"]) == set(res["fp32"]["g"])
+    # the grouped path reports (zero) gradients for experts that received no rows; the per-expert loop reports none
+    assert set(res["fp32"]["g"]) <= set(res["bf16"]["g"])
+    for n in set(res["bf16"]["g"]) - set(res["fp32"]["g"]):
+        assert float(res["bf16"]["g"][n].abs().max()) == 0.0, n
     num = sum(float(((res["bf16"]["g"][n] - g) ** 2).sum()) for n, g in res["fp32"]["g"].items())
     den = sum(float((g ** 2).sum()) for g in res["fp32"]["g"].values())
     assert (num / den) ** 0.5 < 5e-2
