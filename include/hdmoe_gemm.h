@@ -26,10 +26,12 @@ int hdmoe_gconv_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H,
                     const int32_t* ksize_host, const int32_t* wrow_host, const float* scale, int act,
                     const void* residual, float res_a, float res_b, void* stream);
 
-/* Same contract as hdmoe_gconv_fwd, halo-reuse implementation: the zero-padded input window of a strip of output
- * rows is loaded ONCE per tile and every filter tap reads it through a shifted UMMA descriptor (flattened
- * padded-image formulation), removing the k^2-fold L2 re-reads of the per-tap loader.  Any H <= 255, W <= 248
- * (no 128-pixel divisibility requirement); at most 4 distinct kernel sizes per launch. */
+/* Same contract as hdmoe_gconv_fwd, halo-reuse implementation: the zero-padded input window of a tile (a run of up to
+ * three 128-position M-tiles of the flattened padded image) is loaded ONCE and every filter tap reads it through a
+ * shifted UMMA descriptor, removing the k^2-fold L2 re-reads of the per-tap loader.  Any H <= 255, W <= 248 (no
+ * 128-pixel divisibility requirement); at most 4 distinct kernel sizes per launch; Y and residual 32-byte aligned.
+ * Preconditions: row_expert[r] in [0, n_experts) for r < *n_rows_dev.  Tiles are handed out by a device-side counter
+ * that belongs to (device, stream): launches that may run concurrently must be issued on different streams. */
 int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H, int W, int Cin_pad, int Cout,
                      int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev, int n_experts,
                      const int32_t* ksize_host, const int32_t* wrow_host, const float* scale, int act,
@@ -39,7 +41,8 @@ int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H
  *   dW[wrow[e] + tap*Cout + o, c] += sum over rows r of expert e and pixels q of dY[r,q,o] * Xpad[r, q+delta_tap, c]
  * dW is fp32 [w_rows_total, Cin_pad] in the tap-major block layout of the forward operand and must be zeroed by
  * the caller before the first accumulation of a step.  X / dY are NHWC bf16 as in hdmoe_gconv_fwd.
- * Constraints: Cout in {32, 64}; Cin_pad % 32 == 0, <= 256; H % 8 == 0; W even. */
+ * Constraints: Cout in {32, 64}; Cin_pad % 32 == 0, <= 256; H % 4 == 0 (the largest of 32 / 16 / 8 / 4 strip rows that
+ * divides H and fits shared memory is used); W <= 232.  Same stream rule as hdmoe_gconv2_fwd. */
 int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int cap_rows, int H, int W, int Cin_pad, int Cout,
                       int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev, int n_experts,
                       const int32_t* ksize_host, const int32_t* wrow_host, void* stream);
