@@ -27,6 +27,20 @@
 
 namespace hdmoe {
 
+// cycle accounting of issuer warp 0 (-DHDMOE_WG_TRACE, read with tools/dbg_wgrad.py)
+#ifdef HDMOE_WG_TRACE
+__device__ long long wg2_trace[148 * 16];
+#define WGT_DECL long long wt_[7] = {0, 0, 0, 0, 0, 0, 0}; long long wt0_ = clock64(); (void)wt0_
+#define WGT_LAP(i) do { const long long n_ = clock64(); wt_[i] += n_ - wt0_; wt0_ = n_; } while (0)
+#define WGT_CNT(i) do { wt_[i] += 1; } while (0)
+#define WGT_OUT(base) do { for (int q_ = 0; q_ < 7; ++q_) wg2_trace[blockIdx.x * 16 + (base) + q_] = wt_[q_]; } while (0)
+#else
+#define WGT_DECL do { } while (0)
+#define WGT_LAP(i) do { } while (0)
+#define WGT_CNT(i) do { } while (0)
+#define WGT_OUT(base) do { } while (0)
+#endif
+
 constexpr int kW2Issuers = 4;
 constexpr int kW2Threads = 32 * (1 + kW2Issuers + 4);
 constexpr int kW2Classes = 4;
@@ -202,21 +216,27 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             int s = 0, buf = 0;
             uint32_t ph = 0, tph[2] = {0, 0};
             bool need_buf = true;                       // the next stage is the first of a fresh accumulator buffer
+            WGT_DECL;
             for (;;) {
                 const int item = next_item(false);
+                WGT_LAP(0);                             // waiting for an item
                 if (item < 0) break;
+                WGT_CNT(5);
                 walk(item,
                      [&](int r, int e, int kc, int g, int st, int c, bool first) {
                          const int Wp = p.wp[kc], upr = p.upr[kc];
                          const int u_lo = g * p.upg, u_hi = min(p.nunits[kc], u_lo + p.upg);
                          const int nslice = (p.SH * Wp) >> 4;
+                         WGT_LAP(1);                             // walk / decode
                          if (need_buf) {
                              mb_wait(&t_empty[buf], tph[buf] ^ 1);      // the epilogue has drained this buffer
                              tc_fence_after();
                              need_buf = false;
+                             WGT_LAP(4);                         // waiting for the accumulator buffer (flush not hidden)
                          }
                          mb_wait(&full[s], ph);
                          tc_fence_after();
+                         WGT_LAP(2);                             // waiting for the stage's TMA loads
                          const uint32_t a0 = s2u(smem + (size_t)s * stage_bytes) + kW2Lead - (TPM - 1) * ROWA;
                          const uint32_t b0 = s2u(smem + (size_t)s * stage_bytes) + p.a_stage_bytes;
                          const uint64_t ad0 = umma_desc_mn2<ROWA>(a0, ROWA);     // atoms one position row apart
@@ -230,18 +250,21 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                                         !(first && j == 0));
                          }
                          tc_commit(&empty[s]);
+                         WGT_LAP(3);                             // issuing MMAs
                          if (++s == kW2Stages) {
                              s = 0;
                              ph ^= 1;
                          }
                      },
                      [&](int, int, int) {
+                         WGT_CNT(6);
                          tc_commit(&t_full[buf]);           // all accumulators of the group are final
                          tph[buf] ^= 1;
                          buf ^= 1;
                          need_buf = true;
                      });
             }
+            if (me == 0) WGT_OUT(0);
         }
     } else {
         // ============================== epilogue: TMEM -> vector atomics ==============================
@@ -318,6 +341,12 @@ static int launch_wgrad2(const CUtensorMap* ta, const CUtensorMap* tb, const WGr
 
 }  // namespace hdmoe
 using namespace hdmoe;
+
+#ifdef HDMOE_WG_TRACE
+extern "C" int hdmoe_wg_trace_read(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, wg2_trace, sizeof(long long) * 148 * 16);
+}
+#endif
 
 extern "C" int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int cap_rows, int H, int W, int Cin_pad,
                                  int Cout, int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev,

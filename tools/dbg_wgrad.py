@@ -61,8 +61,8 @@ def run(R, H, W, Cin, Cout, ks, counts, time_it=False):
             buf = (C.c_longlong * (148 * 16))()
             lib.hdmoe_wg_trace_read.argtypes = [C.c_void_p]
             lib.hdmoe_wg_trace_read(buf)
-            a = np.array(buf[:], dtype=np.int64).reshape(148, 16)[:, :6]
-            names = ["wait_item", "decode", "wait_tma", "issue", "flush", "n_items"]
+            a = np.array(buf[:], dtype=np.int64).reshape(148, 16)[:, :7]
+            names = ["wait_item", "decode", "wait_tma", "issue", "flush/acc_wait", "n_items", "n_flush"]
             msg += "\n    issuer-0 cycles per CTA (mean / max): " + "  ".join(f"{n} {a[:, i].mean():.0f}/{a[:, i].max()}" for i, n in enumerate(names))
             msg += f"\n    total {a[:, :5].sum(1).mean():.0f} / {a[:, :5].sum(1).max()}"
     print(msg, flush=True)
