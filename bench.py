@@ -333,19 +333,26 @@ def run_ours(args):
     e2e_ms = max_over_ranks(s.elapsed_time(e), world, device) / e2e_steps
     e2e_value = B * world / (e2e_ms / 1e3)
 
+    # every collective is done: release the other ranks before rank 0 measures the single-GPU extras (they must not
+    # sit in an NCCL call for a minute while rank 0 runs the sampler and the CPU baseline)
+    if world > 1:
+        import torch.distributed as dist
+        barrier(world)
+        dist.destroy_process_group()
     line = None
     if rank == 0:
         peaks = load_peaks()
         roof = roofline_gconv(device, peaks, flush)
-        disp = dispatch_sweep(device, peaks, flush, full=args.full_sweep)
-        samp = sampler_throughput(device) if not args.no_sampler else None
+        solo = world == 1                            # the sweeps, the sampler and the CPU baseline are N = 1 extras
+        disp = dispatch_sweep(device, peaks, flush, full=args.full_sweep) if solo or args.full_sweep else None
+        samp = sampler_throughput(device) if solo and not args.no_sampler else None
         cfg_c = None
-        if not args.no_sampler and world == 1:
+        if not args.no_sampler and solo:
             try:
                 cfg_c = config_c_throughput(device)
             except Exception as exc:                  # noqa: BLE001
                 cfg_c = {"error": str(exc)[:200]}
-        cpu = cpu_baseline_train(sample_batch=8, iters=3)
+        cpu = cpu_baseline_train(sample_batch=8, iters=3) if solo else None
         line = {"metric": "denoiser train img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -364,9 +371,6 @@ def run_ours(args):
                 "roofline": roof, "cpu_baseline": cpu, "peaks": peaks["src"],
                 "dispatch": disp, "sampler": samp, "config_c": cfg_c}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
     return line
 
 
