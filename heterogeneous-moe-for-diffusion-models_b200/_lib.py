@@ -63,6 +63,7 @@ PROTOTYPES = {
     "hdmoe_nhwc_split": (_i, [_p, _f, _f, _i, _i, _p, _p, _i64, _p]),
     "hdmoe_nchw_to_nhwc": (_i, [_p, _p, _i64, _i, _i, _i64, _i, _p]),
     "hdmoe_nhwc_to_nchw": (_i, [_p, _p, _i64, _i, _i, _i64, _p]),
+    "hdmoe_lin32_wgrad": (_i, [_p, _p, _p, _i64, _p]),
     "hdmoe_vit_block_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i, _p, _p]),
     "hdmoe_vit_block_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "hdmoe_gn1_relu_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),

@@ -157,7 +157,11 @@ class MP_Attention(nn.Module):
 
     def _proj(self, conv: MP_Conv, x: torch.Tensor, gain) -> torch.Tensor:
         # a 1x1 convolution over (B, C, S, 1) is a linear map over the channel axis of (B, S, C)
-        return F.linear(x, conv.prepared_weight(gain, x.dtype).flatten(1))
+        w = conv.prepared_weight(gain, x.dtype).flatten(1)
+        if x.is_cuda and w.shape[0] == 32 and w.shape[1] == 32:
+            from . import ops
+            return ops.linear32(x, w)          # streaming weight-gradient kernel for the thin trunk projections
+        return F.linear(x, w)
 
     def forward(self, query: torch.Tensor, gain_s: float, gain_t: float, context: Optional[torch.Tensor] = None,
                 time_embedding: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -672,3 +672,37 @@ class _AttnD4(torch.autograd.Function):
 def attention_d4(q, k, v, heads: int, scale: float):
     """softmax(q k^T * scale) v per head for head_dim 4; q [B,Sq,heads*4], k/v [B,Sk,heads*4] fp32."""
     return _AttnD4.apply(q, k, v, heads, scale)
+
+
+# ------------------------------------------------------------------------------------------------ thin projections
+class _Linear32(torch.autograd.Function):
+    """y = x W^T for the 32 -> 32 trunk projections over B*S rows (MP_Attention._proj,
+    models/model_internals.py:364-372,407).  Forward and input gradient stay library GEMMs; the weight gradient
+    dW = dY^T X (a [32, rows] x [rows, 32] product the library runs without split-K, ~120 us) is the streaming
+    kernel csrc/lin_wgrad.cu (~15 us)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return torch.nn.functional.linear(x, w)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = gy.matmul(w)
+        if ctx.needs_input_grad[1]:
+            g2 = gy.reshape(-1, 32).contiguous()
+            x2 = x.reshape(-1, 32).contiguous()
+            gw = torch.zeros(32, 32, dtype=torch.float32, device=x.device)
+            L.check(L.lib().hdmoe_lin32_wgrad(_p(g2), _p(x2), _p(gw), g2.shape[0], _st()), "lin32_wgrad")
+        return gx, gw
+
+
+def linear32(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """F.linear(x, w) with the streaming weight-gradient kernel when it applies (fp32, 32 -> 32, many rows)."""
+    if (x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and tuple(w.shape) == (32, 32)
+            and x.shape[-1] == 32 and x.numel() >= 32 * 4096 and torch.is_grad_enabled() and w.requires_grad):
+        return _Linear32.apply(x, w)
+    return torch.nn.functional.linear(x, w)

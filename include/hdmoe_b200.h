@@ -252,6 +252,13 @@ int hdmoe_vit_block_bwd(const float* tok_in, const float* time, const int32_t* r
                         float* d_aux, hdmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (11) Weight gradient of the thin trunk projections (the 1x1 q / k / v / out projections of MP_Attention._proj,
+ *      models/model_internals.py:364-372,407): dW[32][32] += dY^T X, dY and X [rows][32] fp32, rows = B * S.
+ *      dW must be zeroed by the caller (CTA partials are added with vector atomics).
+ * ---------------------------------------------------------------------------------------------- */
+int hdmoe_lin32_wgrad(const float* dY, const float* X, float* dW, int64_t rows, hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (9) Router trunk normalisation: GroupNorm(num_groups = 1, C) + ReLU [+ AdaptiveAvgPool2d((1,1))] of
  *     Router.hard_route (models/model_components.py:92-103) on channels-last fp32 activations x [B, HW, C].
  *     fwd: y (may be NULL) = relu(gn(x)), pooled (may be NULL) [B, C] = mean over HW of y, stats [B, 2] = (mean, rstd).

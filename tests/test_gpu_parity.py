@@ -836,3 +836,26 @@ def test_config2_64x64_train_step_bf16_grouped_vs_fp32():
     num = sum(float(((res["bf16"]["g"][n] - g) ** 2).sum()) for n, g in res["fp32"]["g"].items())
     den = sum(float((g ** 2).sum()) for g in res["fp32"]["g"].values())
     assert (num / den) ** 0.5 < 5e-2
+
+
+# ------------------------------------------------------------------------------------------------ thin projections
+@pytest.mark.parametrize("rows", [4096, 65536 + 17, 262144])
+def test_linear32_weight_gradient_kernel(rows):
+    """ops.linear32 (csrc/lin_wgrad.cu): the streaming dW = dY^T X kernel of the 32 -> 32 trunk projections against
+    the fp64 product; forward and input gradient are the library GEMM (fp32, no TF32 here)."""
+    from hdmoe_b200 import ops
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        gen = torch.Generator().manual_seed(rows)
+        x = torch.randn(rows, 32, generator=gen).cuda().requires_grad_(True)
+        w = (torch.randn(32, 32, generator=gen) / 6).cuda().requires_grad_(True)
+        gy = torch.randn(rows, 32, generator=gen).cuda()
+        y = ops.linear32(x, w)
+        y.backward(gy)
+        ref_w = (gy.double().t() @ x.detach().double())
+        assert rel_l2(w.grad.cpu().double(), ref_w.cpu()) < 1e-5
+        assert rel_l2(x.grad.cpu(), (gy @ w.detach()).cpu()) < 1e-5
+        assert rel_l2(y.detach().cpu(), (x.detach() @ w.detach().t()).cpu()) < 1e-5
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
