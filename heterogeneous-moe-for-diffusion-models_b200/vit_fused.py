@@ -122,7 +122,7 @@ class FusedVitExperts:
     def __init__(self, experts):
         self.experts = list(experts)
         self.group = prepared.vit_expert_group(self.experts, torch.float32)
-        self.meta = None
+        self.meta, self._meta_base = None, None
 
     def _build_meta(self):
         grp = self.group
@@ -162,8 +162,9 @@ class FusedVitExperts:
         tx32 = None if txr is None else txr.float()
         row_e = plan.row_expert
         with self.group.prepared(training, plan.counts) as pc:
-            if self.meta is None:
-                self._build_meta()
+            if self.meta is None or self._meta_base != self.group.w_hat_flat.data_ptr():
+                self._build_meta()          # first call, or the group's buffers were rebuilt (model moved)
+                self._meta_base = self.group.w_hat_flat.data_ptr()
             # per expert: patchify (+ pos_emb) and the block conditioning vector, selected by the row's expert
             tok, cond = None, t32.new_zeros(R, _TIME)
             zero = torch.zeros((), dtype=torch.float32, device=x32.device)
