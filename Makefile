@@ -17,6 +17,17 @@ $(LIB): $(OBJ)
 	@mkdir -p $(PKG)/lib
 	$(NVCC) -shared -o $@ $(OBJ) -lcudart
 
+# instrumented builds of the persistent tcgen05 kernels (cycle accounting; read by tools/trace_gconv2.py and
+# tools/dbg_wgrad.py with G2LIB= / WGLIB=), and the hardware probes
+TRACEFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -Iinclude -shared
+trace:
+	$(NVCC) $(TRACEFLAGS) -DHDMOE_G2_TRACE -o tools/libg2trace.so $(PKG)/csrc/gconv2.cu $(PKG)/csrc/core.cu -lcudart
+	$(NVCC) $(TRACEFLAGS) -DHDMOE_WG_TRACE -o tools/libwgtrace.so $(PKG)/csrc/gwgrad.cu $(PKG)/csrc/core.cu -lcudart
+	$(NVCC) $(TRACEFLAGS) -DHDMOE_WG_TRACE -o tools/libwg2trace.so $(PKG)/csrc/gwgrad2.cu $(PKG)/csrc/core.cu -lcudart
+probes:
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_rate tools/umma_rate.cu
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_probe tools/umma_probe.cu
+
 clean:
 	rm -rf build $(LIB)
-.PHONY: all clean
+.PHONY: all clean trace probes

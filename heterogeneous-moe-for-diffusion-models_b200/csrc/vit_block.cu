@@ -333,12 +333,6 @@ __device__ __forceinline__ void outer_acc(const float* d, const float* in, float
     }
 }
 
-// LayerNorm forward that also keeps xhat (in place of `out` when `out_xhat` is given separately) and rstd
-__device__ __forceinline__ void layer_norm_save(const float* in, float* out, float* xhat, float* rstd_out,
-                                                const float* __restrict__ gb, int S) {
-    layer_norm(in, out, xhat, rstd_out, gb, S);
-}
-
 // LayerNorm backward: dx[s][c] (+)= rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)), dxh = dy * gamma;
 // d_gamma += sum_s dy * xhat, d_beta += sum_s dy (atomics).  scale_old: dx = scale_old * dx_old + ln_bwd.
 // dy and dx may alias.
