@@ -156,3 +156,33 @@ def test_direct_gradient_handoff_keeps_accumulation_semantics():
     assert p1.grad.data_ptr() != buf.data_ptr() and torch.equal(p1.grad, torch.tensor([[0.0, 1.0], [2.0, 3.0]]))
     buf.zero_()
     assert float(p1.grad.sum()) == 6.0
+
+
+def test_fused_vit_weight_layout_matches_kernel_order():
+    """Host logic of vit_fused.FusedVitExperts: the ten MP_Conv matrices of every (expert, block) lie contiguously in
+    the prepared-weight buffer in the order csrc/vit_block.cu reads them (linear1, q, k, v, out, q_time, k_time,
+    v_time, linear2, linear3 = 19 456 floats), and the aux offsets follow 256 + 8 S^2 per block.  No kernel is run."""
+    import torch
+    from hdmoe_b200 import model_components as mc, vit_fused
+    patches = [4, 8, 8, 16]
+    experts = torch.nn.ModuleList([mc.Vit_expert(num_heads=8, num_groups=4, in_channels=32, seq_ln=(32 // p) ** 2,
+                                                 emb_dim=32, num_blocks=4, patch_size=p, time_dim=64, text_dim=768)
+                                   for p in patches])
+    runner = vit_fused.FusedVitExperts(experts)
+    runner.group._build(torch.device("cpu"))
+    runner._build_meta()                                   # asserts the layout internally
+    meta = runner.meta
+    assert meta.E == 4 and meta.nb == 4 and list(meta.tokens) == [64, 16, 16, 4]
+    o = 0
+    for e, ex in enumerate(experts):
+        for b in range(4):
+            assert meta.a_off[b][e] == o and o % 4 == 0
+            o += 256 + 8 * ex.seq_ln ** 2
+    assert runner._aux().numel() == o
+    for b in range(4):
+        for e in range(4):
+            assert meta.w_off[b][e] % 4 == 0
+            if b:
+                assert meta.w_off[b][e] - meta.w_off[b - 1][e] == vit_fused._WBLOCK
+    # the CPU never takes the fused path (no CPU fallback of the kernels; the composite torch path runs instead)
+    assert not vit_fused.fusable(experts, torch.zeros(2, 32, 32, 32))
