@@ -27,6 +27,7 @@ trace:
 probes:
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_rate tools/umma_rate.cu
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_probe tools/umma_probe.cu
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Iinclude -o tools/umma_tpair_probe tools/umma_tpair_probe.cu
 
 clean:
 	rm -rf build $(LIB)
