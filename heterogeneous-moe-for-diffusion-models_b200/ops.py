@@ -540,18 +540,22 @@ def gconv_raw(x, w_cat, cout: int, w_rows_total: int, row_expert, n_rows_dev, ks
         scale = _f32c(scale)
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == y.shape
-    fn = L.lib().hdmoe_gconv2_fwd if _GCONV_IMPL[0] == 2 else L.lib().hdmoe_gconv_fwd
+    if _GCONV_IMPL[0] == 3 and cout in (32, 64):
+        fn = L.lib().hdmoe_gconv3_fwd
+    else:
+        fn = L.lib().hdmoe_gconv_fwd if _GCONV_IMPL[0] == 1 else L.lib().hdmoe_gconv2_fwd
     L.check(fn(_p(x), _p(w_cat), _p(y), cap, H, W, cin_pad, cout, w_rows_total, _p(row_expert), _p(n_rows_dev), E, ks, wr,
                _p(scale), int(act), _p(residual), float(res_a), float(res_b), _st()), "gconv_fwd")
     return y
 
 
-# 2 = halo-reuse kernel (gconv2.cu, default); 1 = per-tap loader (gconv.cu, kept for A/B measurements)
+# 2 = halo-reuse kernel (gconv2.cu, default); 1 = per-tap loader (gconv.cu, kept for A/B measurements);
+# 3 = EXPERIMENTAL tap-group kernel (gconv3.cu, Cout 32 / 64; other widths use 2) -- not yet validated on hardware
 _GCONV_IMPL = [2]
 
 
 def set_gconv_impl(v: int) -> None:
-    assert v in (1, 2)
+    assert v in (1, 2, 3)
     _GCONV_IMPL[0] = v
 
 
