@@ -422,36 +422,138 @@ def dispatch_sweep(device, peaks, flush, full=False):
     return {"unit": "GB/s", "peak": peaks["hbm"], "best_frac": round(best / peaks["hbm"], 4), "points": out}
 
 
-def roofline_gconv(device, peaks, flush, iters=10):
-    """Dominant hand-written kernel of the train step by FLOPs: the tcgen05 grouped implicit-GEMM convolution.
-    Shape: the most frequent U-Net expert layer at the bench batch (256 rows routed 36/48/75/97 to the 3x3,
-    3x3, 5x5, 5x5 experts), 32x32, Cin = Cout = 64.  flops = sum_e 2*n_e*H*W*Cout*Cin*k_e^2."""
-    from hdmoe_b200 import ops
-    counts, ks = [36, 48, 75, 97], [3, 3, 5, 5]
-    R, H, Cin, Cout = sum(counts), 32, 64, 64
-    row_e = torch.tensor(sum(([e] * c for e, c in enumerate(counts)), []), dtype=torch.int32, device=device)
+# Every MP_Conv of one Unet_expert that runs through the grouped tcgen05 kernels (SURVEY Appendix D, cfg1/cfg2 at 32x32):
+# (Cin, Cout, H = W, k x k conv? (False = 1x1 skip), multiplicity per expert forward).  30 k x k convolutions + 7 skips.
+UNET_LAYERS = [(64, 64, 16, True, 11), (32, 32, 32, True, 8), (64, 64, 32, True, 2), (64, 32, 32, True, 2),
+               (128, 64, 16, True, 2), (32, 32, 16, True, 2), (96, 64, 16, True, 1), (96, 32, 32, True, 1),
+               (33, 32, 32, True, 1), (128, 64, 16, False, 2), (64, 32, 32, False, 2), (32, 64, 16, False, 1),
+               (96, 64, 16, False, 1), (96, 32, 32, False, 1)]
+ROUTED = [36, 48, 75, 97]          # rows per expert at the bench batch (256 rows, the routing of the synthetic batch)
+KSIZES = [3, 3, 5, 5]
+
+
+def _layer_problem(device, cin, cout, H, kxk):
+    """Operands of one grouped layer at the bench routing: NHWC bf16 rows, tap-major operands for forward / data gradient."""
+    ks = KSIZES if kxk else [1, 1, 1, 1]
+    R = sum(ROUTED)
+    cin_pad = cin if cin % 32 == 0 else (cin + 63) // 64 * 64
+    cin_rows = cin if cin % 32 == 0 else cin // 32 * 32
+    row_e = torch.tensor(sum(([e] * c for e, c in enumerate(ROUTED)), []), dtype=torch.int32, device=device)
     n_rows = torch.tensor([R], dtype=torch.int32, device=device)
-    x = torch.randn(R, H, H, Cin, device=device).to(torch.bfloat16)
-    wrow, tot = [], 0
+    x = torch.randn(R, H, H, cin_pad, device=device).to(torch.bfloat16)
+    dy = torch.randn(R, H, H, cout, device=device).to(torch.bfloat16)
+    wrow, wrow_t, tot, tot_t = [], [], 0, 0
     for k in ks:
         wrow.append(tot)
-        tot += k * k * Cout
-    w = (torch.randn(tot, Cin, device=device) / 30).to(torch.bfloat16)
-    us = _time_us(lambda: ops.gconv_raw(x, w, Cout, tot, row_e, n_rows, ks, wrow), flush, iters)
-    flops = sum(2.0 * c * H * H * Cout * Cin * k * k for c, k in zip(counts, ks))
+        wrow_t.append(tot_t)
+        tot += k * k * cout
+        tot_t += k * k * cin_rows
+    w = (torch.randn(tot, cin_pad, device=device) / 30).to(torch.bfloat16)
+    wt = (torch.randn(tot_t, cout, device=device) / 30).to(torch.bfloat16)
+    dw = torch.zeros(tot, cin_pad, device=device)
+    flops = sum(2.0 * c * H * H * cout * cin * k * k for c, k in zip(ROUTED, ks))
+    flops_dg = sum(2.0 * c * H * H * cout * cin_rows * k * k for c, k in zip(ROUTED, ks))
+    return dict(ks=ks, R=R, cin_pad=cin_pad, cin_rows=cin_rows, row_e=row_e, n_rows=n_rows, x=x, dy=dy, wrow=wrow,
+                wrow_t=wrow_t, tot=tot, tot_t=tot_t, w=w, wt=wt, dw=dw, flops=flops, flops_dg=flops_dg)
+
+
+def _cudnn_layer_us(pr, cin, cout, H, flush, iters):
+    """The same layer through the library: one bf16 channels-last F.conv2d per expert on its contiguous row range
+    (what set_grouped_experts(False) runs), forward and backward (data + weight gradient) timed separately."""
+    import torch.nn.functional as F
+    xs, ws, gs = [], [], []
+    lo = 0
+    for n, k in zip(ROUTED, pr["ks"]):
+        xs.append(pr["x"][lo:lo + n, :, :, :cin].permute(0, 3, 1, 2))                 # NCHW view of NHWC memory
+        ws.append((torch.randn(cout, cin, k, k, device=pr["x"].device) / 30).to(torch.bfloat16)
+                  .contiguous(memory_format=torch.channels_last))
+        gs.append(pr["dy"][lo:lo + n].permute(0, 3, 1, 2))
+        lo += n
+
+    def fwd():
+        for x_, w_ in zip(xs, ws):
+            F.conv2d(x_, w_, padding=(w_.shape[-1] - 1) // 2)
+
+    def bwd():
+        for x_, w_, g_ in zip(xs, ws, gs):
+            p_ = (w_.shape[-1] - 1) // 2
+            torch.ops.aten.convolution_backward(g_, x_, w_, None, (1, 1), (p_, p_), (1, 1), False, (0, 0), 1,
+                                                (True, True, False))
+    return _time_us(fwd, flush, iters), _time_us(bwd, flush, iters)
+
+
+def gconv_shape_table(device, peaks, flush, iters=10, with_cudnn=True):
+    """Per-shape and FLOP-weighted aggregate tensor-pipe fractions of the grouped convolution kernels over ONE train step
+    of the U-Net experts: forward + data gradient (gconv) and weight gradient (gwgrad2) of every layer of UNET_LAYERS at
+    the bench routing, each launch timed alone with CUDA events and a cold L2, against the measured burst bf16 peak."""
+    from hdmoe_b200 import ops
+    rows, agg = [], {"fwd": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0], "cudnn_fwd": [0.0, 0.0],
+                     "cudnn_bwd": [0.0, 0.0]}
+    for cin, cout, H, kxk, mult in UNET_LAYERS:
+        pr = _layer_problem(device, cin, cout, H, kxk)
+        us_f = _time_us(lambda: ops.gconv_raw(pr["x"], pr["w"], cout, pr["tot"], pr["row_e"], pr["n_rows"], pr["ks"],
+                                              pr["wrow"]), flush, iters)
+        us_d = _time_us(lambda: ops.gconv_raw(pr["dy"], pr["wt"], pr["cin_rows"], pr["tot_t"], pr["row_e"], pr["n_rows"],
+                                              pr["ks"], pr["wrow_t"]), flush, iters)
+        us_w = _time_us(lambda: ops.gconv_wgrad_raw(pr["x"], pr["dy"], pr["dw"], pr["row_e"], pr["n_rows"], pr["ks"],
+                                                    pr["wrow"]), flush, iters)
+        row = {"cin": cin, "cout": cout, "hw": H, "k": "3,3,5,5" if kxk else "1x1", "mult": mult,
+               "gflop": round(pr["flops"] / 1e9, 2), "fwd_us": round(us_f, 1), "dgrad_us": round(us_d, 1),
+               "wgrad_us": round(us_w, 1), "fwd_frac": round(pr["flops"] / us_f / 1e6 / peaks["bf16"], 3),
+               "dgrad_frac": round(pr["flops_dg"] / us_d / 1e6 / peaks["bf16"], 3),
+               "wgrad_frac": round(pr["flops"] / us_w / 1e6 / peaks["bf16"], 3)}
+        for key, fl, us in (("fwd", pr["flops"], us_f), ("dgrad", pr["flops_dg"], us_d), ("wgrad", pr["flops"], us_w)):
+            agg[key][0] += fl * mult
+            agg[key][1] += us * mult
+        if with_cudnn and kxk:
+            cf, cb = _cudnn_layer_us(pr, cin, cout, H, flush, max(3, iters // 2))
+            row["cudnn_bf16_fwd_us"], row["cudnn_bf16_bwd_us"] = round(cf, 1), round(cb, 1)
+            agg["cudnn_fwd"][0] += pr["flops"] * mult
+            agg["cudnn_fwd"][1] += cf * mult
+            agg["cudnn_bwd"][0] += (pr["flops"] + pr["flops_dg"]) * mult
+            agg["cudnn_bwd"][1] += cb * mult
+        rows.append(row)
+        del pr
+    def frac(fl_us):
+        return round(fl_us[0] / fl_us[1] / 1e6 / peaks["bf16"], 4) if fl_us[1] else None
+    conv = [agg["fwd"][0] + agg["dgrad"][0], agg["fwd"][1] + agg["dgrad"][1]]
+    out = {"layers": rows, "routing": ROUTED,
+           "aggregate": {"gconv_fwd_dgrad_frac": frac(conv), "gconv_fwd_frac": frac(agg["fwd"]),
+                         "gconv_dgrad_frac": frac(agg["dgrad"]), "gwgrad_frac": frac(agg["wgrad"]),
+                         "gconv_us_per_step": round(conv[1], 1), "gwgrad_us_per_step": round(agg["wgrad"][1], 1),
+                         "gflop_per_step_fwd": round(agg["fwd"][0] / 1e9, 1),
+                         "cudnn_bf16_fwd_frac": frac(agg["cudnn_fwd"]), "cudnn_bf16_bwd_frac": frac(agg["cudnn_bwd"]),
+                         "basis": "FLOP-weighted over the 37 grouped launches of one U-Net-expert pass (x multiplicity), "
+                                  "burst bf16 peak " + peaks["src"]}}
+    return out
+
+
+def roofline_gconv(device, peaks, flush, iters=10):
+    """Dominant hand-written kernel of the train step by FLOPs: the tcgen05 grouped implicit-GEMM convolution.
+    Headline shape: the most EXPENSIVE U-Net expert layer, decoders.32x32_up.conv_res1/2 (2 of the 30 k x k
+    convolutions of an expert, 17 % of its FLOPs): 256 rows routed 36/48/75/97 to the 3x3, 3x3, 5x5, 5x5 experts,
+    32x32, Cin = Cout = 64.  flops = sum_e 2*n_e*H*W*Cout*Cin*k_e^2.  `per_shape` / `aggregate` hold every
+    distinct layer of Appendix D and the FLOP-weighted fraction over one step next to the library (cuDNN bf16) on the
+    same layers."""
+    from hdmoe_b200 import ops
+    pr = _layer_problem(device, 64, 64, 32, True)
+    us = _time_us(lambda: ops.gconv_raw(pr["x"], pr["w"], 64, pr["tot"], pr["row_e"], pr["n_rows"], pr["ks"], pr["wrow"]),
+                  flush, iters)
+    flops = pr["flops"]
     ach = flops / us / 1e6
-    # weight gradient of the same layer (gwgrad2_kernel): same flops
-    dy = torch.randn(R, H, H, Cout, device=device).to(torch.bfloat16)
-    dw = torch.zeros(tot, Cin, device=device)
-    us_w = _time_us(lambda: ops.gconv_wgrad_raw(x, dy, dw, row_e, n_rows, ks, wrow), flush, iters)
-    name = "gconv2_fwd_kernel<64,64>"
+    us_w = _time_us(lambda: ops.gconv_wgrad_raw(pr["x"], pr["dy"], pr["dw"], pr["row_e"], pr["n_rows"], pr["ks"],
+                                                pr["wrow"]), flush, iters)
+    impl = ops.get_gconv_impl()
+    name = "gconv3_fwd_kernel<64,64>" if impl == 3 else "gconv2_fwd_kernel<64,64>"
+    table = gconv_shape_table(device, peaks, flush, iters)
     return {"bound": "tensor", "kernel": name + " (256 rows 32x32, Cin=Cout=64, k=3,3,5,5 routed 36/48/75/97)",
             "achieved": round(ach, 1), "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": round(ach / peaks["bf16"], 4),
             "traffic": ncu_traffic(name), "us_per_launch": round(us, 1), "algorithmic_flops": flops,
             "peak_basis": "burst (kernel timed alone), " + peaks["src"],
             "wgrad": {"kernel": "gwgrad2_kernel<64,64> (same layer)", "us_per_launch": round(us_w, 1),
                       "achieved": round(flops / us_w / 1e6, 1), "frac": round(flops / us_w / 1e6 / peaks["bf16"], 4),
-                      "traffic": ncu_traffic("gwgrad2_kernel<64,64>")}}
+                      "traffic": ncu_traffic("gwgrad2_kernel<64,64>")},
+            "aggregate": table["aggregate"], "per_shape": table["layers"]}
 
 
 def ncu_traffic(kernel):

@@ -49,11 +49,9 @@ PROTOTYPES = {
     "hdmoe_edm_heun_euler": (_i, [_p, _p, _i, _p, _p, _i, _f, _f, _f, _f, _p, _p, _p, _i64, _p]),
     "hdmoe_edm_heun_correct": (_i, [_p, _p, _p, _i, _p, _p, _i, _f, _f, _f, _f, _p, _p, _i64, _p]),
     "hdmoe_wprep_fwd": (_i, [_p, _p, _i, _i, _p]),
-    "hdmoe_gconv_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
     "hdmoe_gconv2_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
     "hdmoe_gconv3_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
     "hdmoe_gconv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p]),
-    "hdmoe_gconv_wgrad_v1": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p]),
     "hdmoe_nhwc_pixnorm_silu_fwd": (_i, [_p, _p, _p, _i64, _i, _p]),
     "hdmoe_nhwc_pixnorm_silu_bwd": (_i, [_p, _p, _p, _p, _i64, _i, _p]),
     "hdmoe_nhwc_gain_silu_fwd": (_i, [_p, _p, _p, _i64, _i64, _i, _p]),
@@ -69,8 +67,6 @@ PROTOTYPES = {
     "hdmoe_vit_block_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "hdmoe_gn1_relu_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "hdmoe_gn1_relu_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
-    "hdmoe_attn_d4_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
-    "hdmoe_attn_d4_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "hdmoe_attn_d4_tc_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "hdmoe_attn_d4_tc_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "hdmoe_wprep_fwd_resident": (_i, [_p, _i, _i, _i, _p]),

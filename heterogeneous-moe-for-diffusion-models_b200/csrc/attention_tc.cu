@@ -1,4 +1,4 @@
-// Tensor-core version of the head_dim = 4 trunk attention (attention.cu keeps the CUDA-core kernels).
+// Tensor-core head_dim = 4 trunk attention (the superseded CUDA-core kernels are archived in tools/legacy/attention.cu).
 //
 // With d = 4 the contraction is too thin for tcgen05 tiles, but the warp-level m16n8k8 TF32 MMA fits it exactly:
 // its K = 8 holds the 4 features TWICE, which is used for split-operand ("3xTF32"-style) products instead of
@@ -12,7 +12,7 @@
 // strict fp32 parity.  All three kernels stage the "long" operand of one (batch, head) in shared memory in one
 // layout X = even/odd item arrays of [hi(4) | lo(4)] floats that serves both fragment types without bank
 // conflicts (the odd array is shifted by 4 banks).
-// Same layouts, saved tensors (lse in log2 units of the scaled logits, D = <dO, O>) and ABI shape as attention.cu.
+// Same layouts, saved tensors (lse in log2 units of the scaled logits, D = <dO, O>) as the archived CUDA-core version.
 #include "common.cuh"
 
 namespace hdmoe {

@@ -15,7 +15,7 @@ _SILU_GAIN = 1.0 / 0.596
 # Device-side "this expert received rows" flag (0-dim bool tensor) for sync-free MoE execution: the reference
 # only runs -- and therefore only force-normalises the weights of -- experts with at least one routed sample.
 _ACTIVE = [None]
-_FUSED_ATTN = [True]     # trunk head_dim-4 attention through csrc/attention.cu (False: library SDPA, for A/B tests)
+_FUSED_ATTN = [True]     # trunk head_dim-4 attention through csrc/attention_tc.cu (False: library SDPA, for A/B tests)
 
 
 def set_fused_attention(enabled: bool) -> None:

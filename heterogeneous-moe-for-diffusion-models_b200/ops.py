@@ -540,23 +540,30 @@ def gconv_raw(x, w_cat, cout: int, w_rows_total: int, row_expert, n_rows_dev, ks
         scale = _f32c(scale)
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == y.shape
-    if _GCONV_IMPL[0] == 3 and cout in (32, 64):
-        fn = L.lib().hdmoe_gconv3_fwd
-    else:
-        fn = L.lib().hdmoe_gconv_fwd if _GCONV_IMPL[0] == 1 else L.lib().hdmoe_gconv2_fwd
+    fn = L.lib().hdmoe_gconv3_fwd if (_GCONV_IMPL[0] == 3 and cout in (32, 64)) else L.lib().hdmoe_gconv2_fwd
     L.check(fn(_p(x), _p(w_cat), _p(y), cap, H, W, cin_pad, cout, w_rows_total, _p(row_expert), _p(n_rows_dev), E, ks, wr,
                _p(scale), int(act), _p(residual), float(res_a), float(res_b), _st()), "gconv_fwd")
     return y
 
 
-# 2 = halo-reuse kernel (gconv2.cu, default); 1 = per-tap loader (gconv.cu, kept for A/B measurements);
-# 3 = EXPERIMENTAL tap-group kernel (gconv3.cu, Cout 32 / 64; other widths use 2) -- not yet validated on hardware
+# 2 = halo-reuse kernel (gconv2.cu, default); 3 = tap-group kernel (gconv3.cu: Cout 32 / 64, other widths use 2).
+# Which one is the default is decided per measured shape table (profiles/); 3 needs experimental=True until then.
 _GCONV_IMPL = [2]
 
 
-def set_gconv_impl(v: int) -> None:
-    assert v in (1, 2, 3)
+def set_gconv_impl(v: int, experimental: bool = False) -> None:
+    if v not in (2, 3):
+        raise ValueError("gconv implementation must be 2 or 3")
+    if v == 3 and not experimental and not _GCONV3_VALIDATED:
+        raise RuntimeError("gconv3 is experimental: pass experimental=True")
     _GCONV_IMPL[0] = v
+
+
+def get_gconv_impl() -> int:
+    return _GCONV_IMPL[0]
+
+
+_GCONV3_VALIDATED = False
 
 
 def gconv_wgrad_raw(x, dy, dw, row_expert, n_rows_dev, ksizes, wrows):
@@ -620,15 +627,6 @@ def gn1_relu_supported(channels: int) -> bool:
     return channels % 4 == 0 and 1024 % (channels // 4) == 0
 
 
-# attention implementation: "tc" = warp-MMA tensor-core kernels (csrc/attention_tc.cu), "cc" = CUDA-core kernels
-_ATTN_IMPL = ["tc"]
-
-
-def set_attention_impl(impl: str) -> None:
-    assert impl in ("tc", "cc")
-    _ATTN_IMPL[0] = impl
-
-
 def _attn_split_p() -> int:
     """Strict fp32 (p and dS split into hi + lo) unless TF32 matmuls are enabled, like the library matmuls."""
     return 0 if torch.backends.cuda.matmul.allow_tf32 else 1
@@ -644,32 +642,24 @@ class _AttnD4(torch.autograd.Function):
         assert Cc == heads * 4 and k.shape == (B, Sk, Cc) and v.shape == (B, Sk, Cc)
         o = torch.empty_like(q)
         lse = torch.empty(B, heads, Sq, dtype=torch.float32, device=q.device)
-        impl, split = _ATTN_IMPL[0], _attn_split_p()
-        if impl == "tc":
-            L.check(L.lib().hdmoe_attn_d4_tc_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), B, Sq, Sk, heads, float(scale), split,
-                                                 _st()), "attn_d4_tc_fwd")
-        else:
-            L.check(L.lib().hdmoe_attn_d4_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), B, Sq, Sk, heads, float(scale), _st()),
-                    "attn_d4_fwd")
+        split = _attn_split_p()
+        L.check(L.lib().hdmoe_attn_d4_tc_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), B, Sq, Sk, heads, float(scale), split,
+                                             _st()), "attn_d4_tc_fwd")
         ctx.save_for_backward(q, k, v, o, lse)
-        ctx.meta = (heads, float(scale), impl, split)
+        ctx.meta = (heads, float(scale), split)
         return o
 
     @staticmethod
     def backward(ctx, dO):
         q, k, v, o, lse = ctx.saved_tensors
-        heads, scale, impl, split = ctx.meta
+        heads, scale, split = ctx.meta
         dO = _f32c(dO)
         B, Sq, _ = q.shape
         Sk = k.shape[1]
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         Dbuf = torch.empty_like(lse)
-        if impl == "tc":
-            L.check(L.lib().hdmoe_attn_d4_tc_bwd(_p(q), _p(k), _p(v), _p(o), _p(dO), _p(lse), _p(dq), _p(dk), _p(dv),
-                                                 _p(Dbuf), B, Sq, Sk, heads, scale, split, _st()), "attn_d4_tc_bwd")
-        else:
-            L.check(L.lib().hdmoe_attn_d4_bwd(_p(q), _p(k), _p(v), _p(o), _p(dO), _p(lse), _p(dq), _p(dk), _p(dv), _p(Dbuf),
-                                              B, Sq, Sk, heads, scale, _st()), "attn_d4_bwd")
+        L.check(L.lib().hdmoe_attn_d4_tc_bwd(_p(q), _p(k), _p(v), _p(o), _p(dO), _p(lse), _p(dq), _p(dk), _p(dv),
+                                             _p(Dbuf), B, Sq, Sk, heads, scale, split, _st()), "attn_d4_tc_bwd")
         return dq, dk, dv, None, None
 
 

@@ -161,7 +161,7 @@ int hdmoe_edm_heun_correct(const float* x_hat, const float* x_next, const void* 
  *        force != 0 (training):  w[o,:] <- w[o,:] / (eps + ||w[o,:]|| / sqrt(fan_in))     (in place, Q6)
  *        w_hat[o,:] = w[o,:] / (eps + ||w[o,:]|| / sqrt(fan_in)) * gain / sqrt(fan_in)
  *     Output layout HDMOE_WLAYOUT_SAME keeps [rows][fan_in]; HDMOE_WLAYOUT_TAPS writes the implicit-GEMM
- *     layout [tap][rows][cin_pad] (K-major, zero padded) consumed by hdmoe_gconv_fwd; HDMOE_WLAYOUT_TAPS_T the
+ *     layout [tap][rows][cin_pad] (K-major, zero padded) consumed by hdmoe_gconv2_fwd; HDMOE_WLAYOUT_TAPS_T the
  *     transposed, tap-flipped operand with which the same kernel computes the data gradient.
  * ---------------------------------------------------------------------------------------------- */
 #define HDMOE_WLAYOUT_SAME 0
@@ -210,19 +210,12 @@ int hdmoe_wprep_bwd_multi_resident(const void* descs_dev, int n, int total_rows,
  *     models/model_internals.py:380-404, when there is no rel_pos_bias (cross_attn, cross_attn_text of
  *     models/model_config2.py:279-289).  q [B,Sq,heads*4], k / v [B,Sk,heads*4], o like q, fp32, contiguous.
  *     lse [B,heads,Sq] (log2-domain log-sum-exp of the scaled logits) is saved for the backward;
- *     Dbuf [B,heads,Sq] is backward scratch.  heads <= 8.
+ *     Dbuf [B,heads,Sq] is backward scratch.
  * ---------------------------------------------------------------------------------------------- */
-int hdmoe_attn_d4_fwd(const float* q, const float* k, const float* v, float* o, float* lse, int B, int Sq, int Sk,
-                      int heads, float scale, hdmoe_stream_t stream);
-int hdmoe_attn_d4_bwd(const float* q, const float* k, const float* v, const float* o, const float* dO,
-                      const float* lse, float* dq, float* dk, float* dv, float* Dbuf, int B, int Sq, int Sk,
-                      int heads, float scale, hdmoe_stream_t stream);
-
-/* Tensor-core variant (csrc/attention_tc.cu): warp-level m16n8k8 TF32 MMAs with split (hi + lo) operands for the
+/* csrc/attention_tc.cu: warp-level m16n8k8 TF32 MMAs with split (hi + lo) operands for the
  * logits and for V / K / Q / dO, probabilities kept in registers.  split_p != 0 also splits p and dS into hi + lo
  * (fp32-grade results, used when TF32 matmuls are disabled); split_p == 0 rounds them to TF32 (the setting of the
- * reference's own run with torch.backends.cuda.matmul.allow_tf32).  Same tensors and saved values as above; any
- * number of heads. */
+ * reference's own run with torch.backends.cuda.matmul.allow_tf32).  Any number of heads. */
 int hdmoe_attn_d4_tc_fwd(const float* q, const float* k, const float* v, float* o, float* lse, int B, int Sq, int Sk,
                          int heads, float scale, int split_p, hdmoe_stream_t stream);
 int hdmoe_attn_d4_tc_bwd(const float* q, const float* k, const float* v, const float* o, const float* dO,

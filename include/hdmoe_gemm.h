@@ -20,13 +20,8 @@ extern "C" {
  *   ksize_host / wrow_host: HOST arrays of length n_experts.
  * Fused epilogue:  v = acc * scale[row, c] (scale may be NULL);  v = mp_silu(v) if act == 1;
  *                  out = res_a * residual + res_b * v  if residual != NULL  (mp_sum folded).
- * Constraints: Cout in {32, 64, 96, 128}; Cin_pad % 32 == 0; W | 128; 128 | H*W. */
-int hdmoe_gconv_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H, int W, int Cin_pad, int Cout,
-                    int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev, int n_experts,
-                    const int32_t* ksize_host, const int32_t* wrow_host, const float* scale, int act,
-                    const void* residual, float res_a, float res_b, void* stream);
-
-/* Same contract as hdmoe_gconv_fwd, halo-reuse implementation: the zero-padded input window of a tile (a run of up to
+ * Constraints: Cout in {32, 64, 96, 128}; Cin_pad % 32 == 0. */
+/* Halo-reuse implementation of the contract above: the zero-padded input window of a tile (a run of up to
  * three 128-position M-tiles of the flattened padded image) is loaded ONCE and every filter tap reads it through a
  * shifted UMMA descriptor, removing the k^2-fold L2 re-reads of the per-tap loader.  Any H <= 255, W <= 248 (no
  * 128-pixel divisibility requirement); at most 4 distinct kernel sizes per launch; Y and residual 32-byte aligned.
@@ -50,14 +45,10 @@ int hdmoe_gconv3_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H
 /* Grouped convolution weight gradient (tcgen05, MN-major operands, split-K with vector atomics):
  *   dW[wrow[e] + tap*Cout + o, c] += sum over rows r of expert e and pixels q of dY[r,q,o] * Xpad[r, q+delta_tap, c]
  * dW is fp32 [w_rows_total, Cin_pad] in the tap-major block layout of the forward operand and must be zeroed by
- * the caller before the first accumulation of a step.  X / dY are NHWC bf16 as in hdmoe_gconv_fwd.
+ * the caller before the first accumulation of a step.  X / dY are NHWC bf16 as in hdmoe_gconv2_fwd.
  * Constraints: Cout in {32, 64}; Cin_pad % 32 == 0, <= 256; H % 4 == 0 (the largest of 32 / 16 / 8 / 4 strip rows that
  * divides H and fits shared memory is used); W <= 232.  Same stream rule as hdmoe_gconv2_fwd. */
 int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int cap_rows, int H, int W, int Cin_pad, int Cout,
-                      int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev, int n_experts,
-                      const int32_t* ksize_host, const int32_t* wrow_host, void* stream);
-/* v1 of the same operation (one M = 64 MMA per tap, single accumulator set); kept for A/B measurement. */
-int hdmoe_gconv_wgrad_v1(const void* X, const void* dY, float* dW, int cap_rows, int H, int W, int Cin_pad, int Cout,
                       int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev, int n_experts,
                       const int32_t* ksize_host, const int32_t* wrow_host, void* stream);
 

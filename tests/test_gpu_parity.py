@@ -551,22 +551,20 @@ def test_grouped_tcgen05_unet_experts_match_per_expert_path(train):
 
 
 # ------------------------------------------------------------------------------------------------ trunk attention
-@pytest.mark.parametrize("impl,tf32", [("tc", False), ("tc", True), ("cc", False)])
+@pytest.mark.parametrize("tf32", [False, True])
 @pytest.mark.parametrize("B,Sq,Sk,H", [(2, 1024, 1024, 8), (3, 1024, 77, 8), (2, 100, 37, 2), (1, 4096, 4096, 8),
                                        (2, 1500, 1100, 3)])
-def test_attention_d4_matches_reference_math(B, Sq, Sk, H, impl, tf32):
+def test_attention_d4_matches_reference_math(B, Sq, Sk, H, tf32):
     """softmax(QK^T/sqrt(d))V for d = 4 (models/model_internals.py:380-404, no rel_pos_bias) fwd + bwd, for the
     tensor-core kernels (strict split-operand mode: fp32 tolerance; TF32 mode: p / dS rounded to 10-bit mantissa,
-    tolerance 1e-3) and the CUDA-core kernels."""
+    tolerance 2e-3)."""
     from hdmoe_b200 import ops
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
-    ops.set_attention_impl(impl)
     try:
-        _attention_case(B, Sq, Sk, H, 2e-3 if tf32 else (3e-5 if impl == "tc" else TOL32), 2e-3 if tf32 else (3e-5 if impl == "tc" else 2e-5))
+        _attention_case(B, Sq, Sk, H, 2e-3 if tf32 else 3e-5, 2e-3 if tf32 else 3e-5)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-        ops.set_attention_impl("tc")
 
 
 def _attention_case(B, Sq, Sk, H, tol_out, tol_grad):

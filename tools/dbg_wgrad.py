@@ -28,7 +28,7 @@ def run(R, H, W, Cin, Cout, ks, counts, time_it=False):
     re_d = torch.tensor(row_e, dtype=torch.int32, device=dev); nr_d = torch.tensor([n_rows], dtype=torch.int32, device=dev)
     ks_h = (C.c_int32 * E)(*ks); wr_h = (C.c_int32 * E)(*wrow)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    FN = lib.hdmoe_gconv_wgrad_v1 if os.environ.get('WGV1') else lib.hdmoe_gconv_wgrad
+    FN = lib.hdmoe_gconv_wgrad
     call = lambda: L.check(FN(p(xd), p(dyd), p(dW), R, H, W, Cin, Cout, tot, p(re_d), p(nr_d), E, ks_h, wr_h, st), "wgrad")
     call()
     torch.cuda.synchronize()
