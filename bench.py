@@ -12,8 +12,8 @@ clip_grad_norm_(1.0) + AdamW over ALL parameters.  N>1
 Prints ONE JSON line (see the repo brief for the contract): value = whole-job img/s with inputs resident in
 HBM; e2e = the same metric through the public module API with pinned HOST inputs, H2D copies and the D2H loss
 read inside the timed region; roofline = the dominant hand-written kernel timed live with CUDA events;
-cpu_baseline = the CPU oracle (a port of the reference) timed on this box's host cores on a bounded sample.
-`--impl reference` times only that CPU arm, on all host threads, and prints the same line shape.
+cpu_baseline = the unmodified reference (oracle/_ref; the oracle port if that is absent) timed on this box's host cores
+on a bounded sample.  `--impl reference` times only that CPU arm, on all host threads, and prints the same line shape.
 """
 import argparse
 import json
@@ -353,6 +353,7 @@ def run_ours(args):
             except Exception as exc:                  # noqa: BLE001
                 cfg_c = {"error": str(exc)[:200]}
         cpu = cpu_baseline_train(sample_batch=8, iters=3) if solo else None
+        ref_gpu = ref_cuda_eager(device) if solo and not args.no_sampler else None
         line = {"metric": "denoiser train img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -369,7 +370,7 @@ def run_ours(args):
                         "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3), "last_loss": loss_host},
                 "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu, "peaks": peaks["src"],
-                "dispatch": disp, "sampler": samp, "config_c": cfg_c}
+                "dispatch": disp, "sampler": samp, "config_c": cfg_c, "ref_cuda_eager": ref_gpu}
         print(json.dumps(line), flush=True)
     return line
 
@@ -642,31 +643,80 @@ def config_c_throughput(device, B=64, steps=5):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (a port of the reference's algorithm) on the host cores
+# Reference arm: the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py) on the host cores; the committed
+# oracle port only when _ref is absent.  Same synthetic batch, same init protocol, train mode (dropout on) in both arms.
 # ---------------------------------------------------------------------------------------------------------
-def cpu_baseline_train(sample_batch=8, iters=3, warmup=1):
-    from oracle import hdmoe_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    model = build_model(1, "cpu")
-    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(("freqs", "phases")))
-          for k, v in model.state_dict().items()}
-    params = [v for v in sd.values() if v.requires_grad]
+def _ref_available():
+    from oracle import make_ref
+    return make_ref.available()
+
+
+def build_ref_model(variant, device, res=32, seed=0):
+    """The reference's own preconditioned_HDMOEM with build_model's init protocol (seeded constructor, zero-init
+    parameters re-drawn from N(0, 0.3^2))."""
+    from oracle import make_ref
+    P1, P2, _, _, _ = make_ref.import_ref()
+    torch.manual_seed(seed)
+    model = (P1 if variant == 1 else P2)(**dict(FULL, IN_img_resolution=res))
+    gen = torch.Generator().manual_seed(seed + 100)
+    with torch.no_grad():
+        for p in model.parameters():
+            if float(p.abs().max()) == 0:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
+    return model.to(device)
+
+
+def _ref_train_step_fn(model, b, variant=1):
+    from oracle import make_ref
+    crit = make_ref.import_ref()[2](**LOSS)
+    params = list(model.parameters())
     opt = torch.optim.AdamW(params, lr=5e-4)
-    b = synth_batch(sample_batch, 32, 0, "cpu")
-    gen = torch.Generator().manual_seed(7)
+    kw = dict(transition_point=P_MEAN, softness=P_STD) if variant == 2 else {}
 
     def step():
-        noise = {"scaling": torch.randn(sample_batch, 2, generator=gen),
-                 "vit": torch.randn(sample_batch, 4, generator=gen), "unet": torch.randn(sample_batch, 4, generator=gen)}
-        with O.training_mode():
-            out = O.preconditioned(sd, FULL, b["x"], b["sigma"], b["text"], b["um"], b["vm"], zeta=2.0,
-                                   return_log_var=True, noise=noise, variant=1)
-        loss = O.edm_loss(b["x0"], out, 4, LOSS["Unet_bal"], LOSS["vit_bal"], LOSS["z_bal"])["loss"]
-        opt.zero_grad(set_to_none=True)
+        out = model(x=b["x"], sigma=b["sigma"], text_emb=b["text"], Unet_router_mask=b["um"], Vit_router_mask=b["vm"],
+                    zeta=2.0, return_log_var=True, **kw)
+        loss = crit(sigma_vec=b["sigma"], x=b["x0"], sigma=b["sigma"], out_model=out)["loss"]
+        opt.zero_grad()
         loss.backward()
         torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
+        return loss
+    return step
+
+
+def cpu_baseline_train(sample_batch=8, iters=3, warmup=1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = synth_batch(sample_batch, 32, 0, "cpu")
+    if _ref_available():
+        model = build_ref_model(1, "cpu")
+        model.train()
+        step = _ref_train_step_fn(model, b)
+        kind = "reference"
+        what = "UNMODIFIED reference (oracle/_ref: models/model_config1.py + Utils/utils.py EDM_LOSS), train mode"
+    else:
+        from oracle import hdmoe_oracle as O
+        model = build_model(1, "cpu")
+        sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(("freqs", "phases")))
+              for k, v in model.state_dict().items()}
+        params = [v for v in sd.values() if v.requires_grad]
+        opt = torch.optim.AdamW(params, lr=5e-4)
+        gen = torch.Generator().manual_seed(7)
+
+        def step():
+            noise = {"scaling": torch.randn(sample_batch, 2, generator=gen),
+                     "vit": torch.randn(sample_batch, 4, generator=gen), "unet": torch.randn(sample_batch, 4, generator=gen)}
+            with O.training_mode():
+                out = O.preconditioned(sd, FULL, b["x"], b["sigma"], b["text"], b["um"], b["vm"], zeta=2.0,
+                                       return_log_var=True, noise=noise, variant=1)
+            loss = O.edm_loss(b["x0"], out, 4, LOSS["Unet_bal"], LOSS["vit_bal"], LOSS["z_bal"])["loss"]
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+        kind = "port"
+        what = "oracle (CPU port of the reference; oracle/_ref absent), dropout off"
 
     for _ in range(warmup):
         step()
@@ -674,9 +724,45 @@ def cpu_baseline_train(sample_batch=8, iters=3, warmup=1):
     for _ in range(iters):
         step()
     dt = (time.perf_counter() - t0) / iters
-    return {"value": round(sample_batch / dt, 3), "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": f"oracle (CPU port of the reference) model_config1 train step, batch {sample_batch}, fp32, "
-                      f"{iters} steps after {warmup} warm-up, dropout off", "s_per_step": round(dt, 3)}
+    return {"value": round(sample_batch / dt, 3), "unit": "img/s", "cores": cores, "kind": kind,
+            "sample": f"{what}: model_config1 train step (fwd+EDM_LOSS+bwd+clip+AdamW), batch {sample_batch}, fp32, "
+                      f"{iters} steps after {warmup} warm-up", "s_per_step": round(dt, 3)}
+
+
+def ref_cuda_eager(device, variant=1, B=256, res=32, iters=3, warmup=2):
+    """Same-box GPU bar: the unmodified reference in eager CUDA fp32 (TF32 matmul / cuDNN on, as bench.py sets
+    for the whole process) on this B200, same workload and inputs as the headline.  None when oracle/_ref is absent."""
+    if not _ref_available():
+        return None
+    for batch in (B, B // 4):
+        try:
+            model = build_ref_model(variant, device, res)
+            model.train()
+            b = {k: v.to(device) for k, v in synth_batch(batch, res, 0, device).items()}
+            step = _ref_train_step_fn(model, b, variant)
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                loss = step()
+            c.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(c) / iters
+            peak = torch.cuda.max_memory_allocated(device) / 2 ** 30
+            del model, step, b
+            torch.cuda.empty_cache()
+            return {"metric": "denoiser train img/s", "value": round(batch / (ms / 1e3), 1), "unit": "img/s",
+                    "ms_per_step": round(ms, 2), "batch": batch, "kind": "reference (oracle/_ref) eager CUDA fp32, TF32 on",
+                    "workload": f"model_config{variant} train step {res}x{res}", "finite": bool(torch.isfinite(loss)),
+                    "peak_mem_GiB": round(peak, 1)}
+        except torch.cuda.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            continue
+        except Exception as exc:                        # noqa: BLE001
+            return {"error": str(exc)[:200]}
+    return {"error": "out of memory at every tried batch"}
 
 
 def run_reference(args):

@@ -38,12 +38,64 @@ class EDM_Sampler:
 
     def denoise(self, x, sigma, text_emb, transition_mean, softness, uncond_text_emb=None):
         """D(x; sigma) with classifier-free guidance folded in: ref.lerp(cond, guidance)."""
+        if self.use_cuda_graph and isinstance(self.model, _Native) and isinstance(self.gnet, _Native) and x.is_cuda:
+            # the evaluation sample() replays: preconditioned input -> graphed network(s) -> c_skip / c_out mix
+            with torch.no_grad():
+                sd = float(getattr(self.model, "sigma_data", 0.5))
+                guided = self.guide != 1.0
+                g_emb = uncond_text_emb if uncond_text_emb is not None else text_emb
+                sig = torch.as_tensor(sigma, dtype=torch.float32, device=x.device).reshape(())
+                x_in = ops.edm_precond_in(x.to(torch.float32), sig, sd)
+                F, Fg = self._eval_graphed(x_in, sig, text_emb, g_emb, transition_mean, softness, guided)
+                D_x = ops.edm_precond_out(x_in, F.to(torch.float32), sig, sd).to(self.dtype)
+                if not guided:
+                    return D_x
+                return ops.edm_precond_out(x_in, Fg.to(torch.float32), sig, sd).to(self.dtype).lerp(D_x, self.guide)
         D_x = self._call(self.model, x, sigma, text_emb, transition_mean, softness).to(self.dtype)
         if self.guide == 1.0:
             return D_x
         emb = uncond_text_emb if uncond_text_emb is not None else text_emb
         ref = self._call(self.gnet, x, sigma, emb, transition_mean, softness).to(self.dtype)
         return ref.lerp(D_x, self.guide)
+
+    def _eval_graphed(self, x_in, sigma_t, text_emb, g_emb, transition_mean, softness, guided):
+        """One (or, guided, two) raw network evaluation(s) through a recorded CUDA graph.  Everything the capture
+        bakes in is part of the cache key: shapes / dtype, the conditioning tensors (identity AND shape -- the entry
+        keeps them alive so a recycled address cannot alias), the python scalars transition_mean / softness, and the
+        train / eval state of both networks."""
+        key = (tuple(x_in.shape), x_in.dtype, text_emb.data_ptr() if text_emb is not None else 0,
+               tuple(text_emb.shape) if text_emb is not None else None,
+               (g_emb.data_ptr(), tuple(g_emb.shape)) if (guided and g_emb is not None) else None, guided,
+               float(transition_mean), float(softness), bool(self.model.training), bool(self.gnet.training),
+               id(self.model), id(self.gnet))
+        ent = self._graphs.get(key)
+        if ent is None:
+            st_x, st_s = x_in.clone(), sigma_t.detach().clone().reshape(())
+            kw = dict(precomputed_x_in=st_x, raw_output=True)
+
+            def run():
+                F_ = self._call(self.model, st_x, st_s, text_emb, transition_mean, softness, **kw)
+                Fg_ = self._call(self.gnet, st_x, st_s, g_emb, transition_mean, softness, **kw) if guided else None
+                return F_, Fg_
+
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    run()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                outs = run()
+            self.nfe -= 3 * (2 if guided else 1)        # warm-up / capture calls are not function evaluations
+            ent = (graph, st_x, st_s, outs, (text_emb, g_emb))   # the conditioning tensors stay alive with the graph
+            self._graphs[key] = ent
+        graph, st_x, st_s, outs, _keep = ent
+        st_x.copy_(x_in)
+        st_s.copy_(sigma_t.reshape(()))
+        graph.replay()
+        self.nfe += 2 if guided else 1
+        return outs
 
     def t_steps(self) -> torch.Tensor:
         """Karras rho-schedule with a trailing zero (Utils/EDM_sampler.py:82-87), fp32 on the host."""
@@ -67,41 +119,10 @@ class EDM_Sampler:
         f32 = np.float32
         x_next = noise.to(self.dtype) * t_dev[0]
 
-        def eval_graphed(x_in, sigma_t):
-            key = (tuple(x_in.shape), x_in.dtype, text_emb.data_ptr(), g_emb.data_ptr() if guided else 0, guided)
-            ent = self._graphs.get(key)
-            if ent is None:
-                st_x, st_s = x_in.clone(), sigma_t.detach().clone().reshape(())
-                kw = dict(precomputed_x_in=st_x, raw_output=True)
-
-                def run():
-                    F_ = self._call(self.model, st_x, st_s, text_emb, transition_mean, softness, **kw)
-                    Fg_ = self._call(self.gnet, st_x, st_s, g_emb, transition_mean, softness, **kw) if guided else None
-                    return F_, Fg_
-
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    for _ in range(2):
-                        run()
-                torch.cuda.current_stream().wait_stream(side)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=side):
-                    outs = run()
-                self.nfe -= 3 * (2 if guided else 1)        # warm-up / capture calls are not function evaluations
-                ent = (graph, st_x, st_s, outs)
-                self._graphs[key] = ent
-            graph, st_x, st_s, outs = ent
-            st_x.copy_(x_in)
-            st_s.copy_(sigma_t.reshape(()))
-            graph.replay()
-            self.nfe += 2 if guided else 1
-            return outs
-
         def evaluate(x_in_or_x, sigma_t):
             """-> (F, F_guide): raw network outputs (native) or denoised estimates (foreign model)."""
             if native and self.use_cuda_graph:
-                return eval_graphed(x_in_or_x, sigma_t)
+                return self._eval_graphed(x_in_or_x, sigma_t, text_emb, g_emb, transition_mean, softness, guided)
             if native:
                 kw = dict(precomputed_x_in=x_in_or_x, raw_output=True)
                 F = self._call(self.model, x_in_or_x, sigma_t, text_emb, transition_mean, softness, **kw)

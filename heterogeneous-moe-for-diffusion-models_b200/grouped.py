@@ -76,13 +76,15 @@ class _GConvFn(torch.autograd.Function):
                           layer.wrow)
         ctx.save_for_backward(x)
         ctx.runner, ctx.li = runner, li
+        ctx.plan, ctx.gen = plan, runner.generation
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         runner, layer = ctx.runner, ctx.runner.layers[ctx.li]
-        plan = runner.plan
+        runner.check_generation(ctx.gen)
+        plan = ctx.plan
         dy = dy.contiguous()
         dx = None
         if ctx.needs_input_grad[0]:
@@ -90,7 +92,7 @@ class _GConvFn(torch.autograd.Function):
                                layer.ks, layer.wrow_t)
             if layer.cin_rows < layer.cin_pad:
                 dx = F.pad(dx, (0, layer.cin_pad - layer.cin_rows))
-        runner.weight_grad_async(layer, x, dy)
+        runner.weight_grad_async(layer, x, dy, plan)
         return dx, torch.zeros_like(ctx.runner.token_like), None, None
 
 
@@ -101,13 +103,14 @@ class _PrepWeights(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, training, *params):
         runner._run_prep(training)
-        ctx.runner = runner
+        ctx.runner, ctx.gen = runner, runner.generation
         token = torch.zeros(1, device=params[0].device)
         outs = (token, runner.lin_noise.clone(), runner.lin_text.clone(), runner.lin_emb.clone())
         return outs
 
     @staticmethod
     def backward(ctx, g_token, g_noise, g_text, g_emb):
+        ctx.runner.check_generation(ctx.gen)
         grads = ctx.runner._run_prep_backward(g_noise, g_text, g_emb)
         return (None, None, *grads)
 
@@ -163,6 +166,18 @@ class GroupedUnetExperts:
         self._wg_stream, self._wg_pending = None, False
         self.plan = None
         self.token_like = None
+        # The operand buffers, the weight-gradient accumulator and the W-PREP tables are persistent (pointer-stable for
+        # CUDA-graph replay) and therefore hold the state of ONE forward: `generation` counts forwards that took the
+        # autograd path, and every backward node checks that it belongs to the latest one.
+        self.generation = 0
+
+    def check_generation(self, gen: int) -> None:
+        if gen != self.generation:
+            raise RuntimeError(
+                "hdmoe_b200 grouped experts: backward of forward #%d after forward #%d ran -- the grouped path keeps the "
+                "prepared weights and gradient accumulators of one forward at a time (one backward per forward; for "
+                "several micro-batches call backward before the next forward, or use set_grouped_experts(False))"
+                % (gen, self.generation))
 
     # ------------------------------------------------------------------------------------------ buffers
     def _params(self):
@@ -306,16 +321,16 @@ class GroupedUnetExperts:
         return prepared.deliver_grads(self._params(), views)
 
     # ------------------------------------------------------------------------------------------ wgrad
-    def weight_grad(self, layer: _ConvLayer, x, dy):
+    def weight_grad(self, layer: _ConvLayer, x, dy, plan=None):
         """layer.dw (fp32, tap-major blocks) += grouped weight gradient: one tcgen05 launch for all experts."""
-        p = self.plan
+        p = plan if plan is not None else self.plan
         ops.gconv_wgrad_raw(x, dy, layer.dw, p.row_expert, p.n_rows_dev, layer.ks, layer.wrow)
 
-    def weight_grad_async(self, layer, x, dy):
+    def weight_grad_async(self, layer, x, dy, plan=None):
         """Weight gradient on a side stream: nothing on the data-gradient chain depends on it; the join is in
         _run_prep_backward (the W-PREP backward node runs after every convolution's backward)."""
         if not _WGRAD_STREAM[0]:
-            return self.weight_grad(layer, x, dy)
+            return self.weight_grad(layer, x, dy, plan)
         cur = torch.cuda.current_stream()
         if self._wg_stream is None:
             self._wg_stream = torch.cuda.Stream(device=x.device)
@@ -324,7 +339,7 @@ class GroupedUnetExperts:
         x.record_stream(side)
         dy.record_stream(side)
         with torch.cuda.stream(side):
-            self.weight_grad(layer, x, dy)
+            self.weight_grad(layer, x, dy, plan)
         self._wg_pending = True
 
     # ------------------------------------------------------------------------------------------ forward
@@ -356,8 +371,13 @@ class GroupedUnetExperts:
             self._build(dev)
         self.plan = plan
         self.token_like = torch.zeros(1, device=dev)
-        need_grad = training and torch.is_grad_enabled()
+        # autograd path whenever a gradient can flow (independent of .training: eval-mode forwards under autograd
+        # propagate to the input and the expert parameters like the reference); `training` only selects the forced
+        # weight normalisation (Q6) and dropout
+        need_grad = torch.is_grad_enabled() and (x_rows.requires_grad or time_rows.requires_grad
+                                                 or any(p_.requires_grad for p_ in self._params()))
         if need_grad:
+            self.generation += 1
             token, Wn, Wt, We = _PrepWeights.apply(self, training, *self._params())
         else:
             self._run_prep(training)
@@ -398,7 +418,7 @@ class GroupedUnetExperts:
             if use:
                 y = self._conv(a, s["res1"], token, True)
                 y = nhwc.gain_silu(y, g)
-                if s["dropout"]:
+                if training and s["dropout"]:
                     y = F.dropout(y, p=s["dropout"])
                 y = self._conv(y, s["res2"], token, True)
                 if s["type"] == "dec" and s["skip"] is not None:
@@ -406,6 +426,8 @@ class GroupedUnetExperts:
                 x = nhwc.mp_sum(x, y, t)
             else:   # fused epilogues: mp_silu(conv * (1+emb)) and mp_sum(x, conv, t)
                 y = self._conv(a, s["res1"], token, False, scale=g, act=1)
+                if training and s["dropout"]:             # train mode under no_grad still drops (as the reference)
+                    y = F.dropout(y, p=s["dropout"])
                 if s["type"] == "dec" and s["skip"] is not None:
                     x = self._conv(x, s["skip"], token, False)
                 x = self._conv(y, s["res2"], token, False, residual=x.contiguous(), res_a=(1 - t) / c, res_b=t / c)

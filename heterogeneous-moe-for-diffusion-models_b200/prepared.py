@@ -60,12 +60,19 @@ def lookup(module, gain) -> Optional[torch.Tensor]:
 class _PrepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, group, training, *weights):
+        group.generation += 1
         group._run_fwd(training)
-        ctx.group = group
+        ctx.group, ctx.gen = group, group.generation
         return tuple(v.view_as(v) for v in group.w_hat_views)
 
     @staticmethod
     def backward(ctx, *grads):
+        if ctx.gen != ctx.group.generation:
+            # the prepared weights are overwritten in place by the next forward's W-PREP launch: the views autograd
+            # saved for this backward no longer hold this forward's values
+            raise RuntimeError("hdmoe_b200 PreparedGroup: backward of forward #%d after forward #%d ran (one backward "
+                               "per forward; call backward before the next forward, or set_trunk_weight_prep(False))"
+                               % (ctx.gen, ctx.group.generation))
         return (None, None, *ctx.group._run_bwd(grads))
 
 
@@ -80,6 +87,7 @@ class PreparedGroup:
         self.n_experts = n_experts
         self.out_dtype = out_dtype
         self._dev = None
+        self.generation = 0          # forwards through the autograd path (buffers hold ONE forward's state)
 
     def _build(self, dev):
         n = sum(m.weights.numel() for m in self.mods)

@@ -168,3 +168,70 @@ def test_reference_invariants():
     sp, _, _, _ = O.router_gate_from_logits(torch.randn(8, 6).masked_fill(m == 0, float("-inf")), 2)
     assert (sp[:, 2] == 0).all()
     assert float(O.z_loss(torch.full((4, 3), 5.0))) < float(O.z_loss(torch.full((4, 3), 8.0)))
+
+
+# ------------------------------------------------------------------------------------------------ shipped configuration
+def full_weights_from_seed(variant, seed=0):
+    """The state_dict the fixture's model had: the constructor's draws under torch.manual_seed(seed) (the drop-in modules
+    consume the RNG in the reference's order) + the zero-init re-draw of tools/make_golden.py."""
+    from conftest import FULL
+    from hdmoe_b200 import model_config1, model_config2
+    torch.manual_seed(seed)
+    model = (model_config2 if variant == 2 else model_config1).preconditioned_HDMOEM(**FULL)
+    gen = torch.Generator().manual_seed(seed + 100)
+    with torch.no_grad():
+        for _, p in model.named_parameters():
+            if p.abs().max() == 0:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
+    return model
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_full_config_train_step_matches_reference(variant):
+    """Pins the oracle to the live reference at the SHIPPED hyper-parameters (Utils/configs.py:3-35), train mode: outputs,
+    routing, loss terms, input gradient, the norm of every parameter gradient, selected full gradients, post-step
+    weights.  The 9 M weights are reproduced from the seed; their per-tensor norms are checked against the fixture."""
+    import contextlib
+    from conftest import FULL
+    g = load_golden(f"full_cfg{variant}_train")
+    model = full_weights_from_seed(variant, int(g["meta.seed"]))
+    names = [n for n, _ in model.named_parameters()]
+    w_norms = torch.stack([p.detach().double().norm() for _, p in model.named_parameters()])
+    assert torch.allclose(w_norms, g["meta.w_norms"], rtol=1e-12, atol=0), "constructor RNG order differs from the reference"
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(("freqs", "phases")))
+          for k, v in model.state_dict().items()}
+    draws = [g[f"noise.{i}"] for i in range(g["meta.n_noise"])]
+    noise = ({"scaling": draws[0], "vit": draws[1], "unet": draws[2]} if variant == 1
+             else {"vit": draws[0], "unet": draws[1]})
+    x = g["in.x"].clone().requires_grad_(True)
+    with O.training_mode():
+        out = O.preconditioned(sd, FULL, x, g["in.sigma"], g["in.text"], g["in.unet_mask"], g["in.vit_mask"],
+                               zeta=g["in.zeta"], transition_point=-1.2, softness=1.6, return_log_var=True, noise=noise,
+                               variant=variant)
+    for key in ("denoised", "Unet_router_loss", "vit_router_loss", "scaling_net_out", "out_gate", "log_var"):
+        assert rel_l2(out[key], g["out." + key]) < 1e-5, key
+    for key in ("Unet_raw", "vit_raw"):
+        ref = g["out." + key]
+        assert torch.equal(torch.isinf(out[key]), torch.isinf(ref))
+        assert torch.equal(out[key].argmax(1), ref.argmax(1))
+    loss = O.edm_loss(g["in.x0"], out, 4, 0.05, 0.1, 0.005)
+    for key in ("loss", "denoising", "balance", "z_loss", "pure_loss"):
+        assert abs(float(loss[key]) - float(g["loss." + key])) < 1e-5 * max(1.0, abs(float(g["loss." + key]))), key
+    loss["loss"].backward()
+    assert rel_l2(x.grad, g["grad.x"]) < 1e-4
+    gn = torch.stack([(sd[n].grad.double().norm() if sd[n].grad is not None else torch.zeros((), dtype=torch.float64))
+                      for n in names])
+    ref_gn = g["gradnorm.all"]
+    big = ref_gn > 1e-6 * ref_gn.max()
+    assert float(((gn - ref_gn).abs() / ref_gn.clamp_min(1e-30))[big].max()) < 2e-3
+    assert float(gn[~big].max() if (~big).any() else 0.0) < 1e-5 * float(ref_gn.max())
+    for k_, v in g.items():
+        if k_.startswith("grad.") and k_ != "grad.x":
+            got = sd[k_[5:]].grad
+            got = torch.zeros_like(v) if got is None else got
+            if float(v.abs().max()) == 0:
+                assert float(got.abs().max()) < 1e-9, k_
+            else:
+                assert rel_l2(got, v) < 2e-4, k_
+        if k_.startswith("sd_after."):
+            assert rel_l2(sd[k_[9:]].detach(), v) < 1e-6, k_

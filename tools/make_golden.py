@@ -347,6 +347,79 @@ def primitives_case():
     print("primitives ok")
 
 
+FULL = dict(IN_in_channels=4, IN_img_resolution=32, internal_channels=32, time_emb_dim=64, text_emb_dim=768,
+            num_experts=4, top_k=1, Fourier_bandwidth=1.0, VIT_num_blocks=4, VIT_patch_sizes=[4, 8, 8, 16],
+            VIT_num_groups=4, VIT_num_heads=8, VIT_emb_size=32, Unet_num_blocks=2, Unet_channel_mult=[1, 2],
+            Unet_kernel_sizes=[(3, 3), (3, 3), (5, 5), (5, 5)], Unet_model_channels=32, Unet_channel_mult_emb=2,
+            Unet_label_balance=0.5, Unet_concat_balance=0.5, sigma_data=0.5, log_var_channels=32)
+FULL_GRAD_KEYS = ("net.input_proj.weights", "net.Unet_router.linear.weights", "net.Unet_router.hard_route.0.weights",
+                  "net.vit_router.time_linear.weights", "net.Unet_experts.0.out_gain", "net.Unet_experts.3.out_gain",
+                  "net.Unet_experts.1.encoders.32x32_conv.weights",
+                  "net.Unet_experts.0.encoders.16x16_block0.conv_res1.weights",
+                  "net.Unet_experts.3.decoders.32x32_block2.conv_skip.weights",
+                  "net.Unet_experts.2.map_noise.weights", "net.VIT_experts.0.diffit.2.linear2.weights",
+                  "net.VIT_experts.2.diffit.0.TMSA.rel_pos_bias", "net.VIT_experts.0.patch.weight",
+                  "net.cross_attn.q_proj.weights", "net.cross_attn_text.k_proj.weights", "net.alpha_txt",
+                  "net.gate1.weights", "log_var_linear.weights", "net.output_proj.weights")
+
+
+def full_case(name, variant, B=4, seed=0):
+    """One train-mode step of the SHIPPED hyper-parameters (Utils/configs.py:3-35) on the unmodified reference.  Weights are
+    NOT stored (9 M parameters): they are the constructor's draw under torch.manual_seed(seed) + the zero-init re-draw,
+    which the drop-in modules reproduce (RNG order is part of the boundary); per-tensor norms are stored to verify that.
+    Outputs only: the output dict, loss terms, grad.x, the L2 norm of every parameter gradient, a few full gradients and
+    a few post-step weights (quirk Q6)."""
+    mod = c2 if variant == 2 else c1
+    torch.manual_seed(seed)
+    model = mod.preconditioned_HDMOEM(**FULL)
+    gen = torch.Generator().manual_seed(seed + 100)
+    randomize_zero_init(model, gen)
+    set_dropout_zero(model)
+    model.train()
+    names = [n for n, _ in model.named_parameters()]
+    w_norms = torch.stack([p.detach().double().norm() for _, p in model.named_parameters()])
+    gen = torch.Generator().manual_seed(seed + 200)
+    x0 = torch.randn(B, 4, 32, 32, generator=gen) * 0.5
+    sigma = torch.exp(torch.randn(B, 1, 1, 1, generator=gen) * 1.6 - 1.2).clamp(0.002, 80.0)
+    x = (x0 + sigma * torch.randn(x0.shape, generator=gen)).requires_grad_(True)
+    text = torch.randn(B, 8, 768, generator=gen)
+    um = torch.ones(B, 4)
+    vm = torch.ones(B, 4)
+    um[0, 1] = 0.0
+    vm[1, 2] = 0.0
+    zeta = 0.7
+    kw = dict(x=x, sigma=sigma, text_emb=text, Unet_router_mask=um, Vit_router_mask=vm, zeta=zeta, return_log_var=True)
+    if variant == 2:
+        kw.update(transition_point=-1.2, softness=1.6)
+    with NoiseTap() as tap:
+        out = model(**kw)
+    crit = U.EDM_LOSS(num_experts=4, sigma_data=0.5, Unet_bal=0.05, vit_bal=0.1, z_bal=0.005, prior_bal=0.0)
+    loss = crit(sigma_vec=sigma, x=x0, sigma=sigma, out_model=out)
+    loss["loss"].backward()
+    rec = {"in.x": x, "in.x0": x0, "in.sigma": sigma, "in.text": text, "in.unet_mask": um, "in.vit_mask": vm,
+           "in.zeta": zeta, "meta.variant": variant, "meta.top_k": 1, "meta.train": 1, "meta.seed": seed,
+           "meta.w_norms": w_norms}
+    for k, v in out.items():
+        rec["out." + k] = v
+    for k, v in loss.items():
+        if torch.is_tensor(v):
+            rec["loss." + k] = v
+    for i, d in enumerate(tap.draws):
+        rec[f"noise.{i}"] = d
+    rec["meta.n_noise"] = len(tap.draws)
+    rec["grad.x"] = x.grad
+    named = dict(model.named_parameters())
+    rec["gradnorm.all"] = torch.stack([(named[n].grad.double().norm() if named[n].grad is not None
+                                        else torch.zeros((), dtype=torch.float64)) for n in names])
+    for gk in FULL_GRAD_KEYS:
+        g = named[gk].grad
+        rec["grad." + gk] = g if g is not None else torch.zeros_like(named[gk])
+    for k in ("net.input_proj.weights", "net.Unet_router.hard_route.0.weights", "net.gate2.weights"):
+        rec["sd_after." + k] = model.state_dict()[k]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **npify(rec))
+    print(name, "loss", float(loss["loss"]), "routing", out["Unet_raw"].argmax(1).tolist(), out["vit_raw"].argmax(1).tolist())
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
@@ -360,5 +433,7 @@ if __name__ == "__main__":
     moe_identity_case()
     producers_case()
     primitives_case()
+    full_case("full_cfg1_train", 1)
+    full_case("full_cfg2_train", 2)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
