@@ -12,6 +12,7 @@ from ._denoiser import (disable_expert_parallel, enable_expert_parallel, get_exp
                         set_expert_dtype, set_grouped_experts, set_branch_streams)
 from .EDM_sampler import EDM_Sampler  # noqa: F401
 from .ops import set_gconv_impl  # noqa: F401
+from .router_trunk import set_router_tcgen05_trunk  # noqa: F401
 
 __all__ = ["ops", "model_internals", "model_components", "model_config1", "model_config2", "EDM_sampler", "utils",
            "EDM_Sampler", "set_expert_dtype", "get_expert_dtype", "set_grouped_experts", "set_branch_streams"]

@@ -272,15 +272,32 @@ class HDMOEM(nn.Module):
         noise = noise or {}
         if x.is_cuda and _TRUNK_PREP[0]:
             from . import prepared
-            grp = self.__dict__.get("_hdmoe_trunk_group")
+            tc_trunk = self._router_trunk(x) is not None
+            key = "_hdmoe_trunk_group" + ("_tc" if tc_trunk else "")
+            grp = self.__dict__.get(key)
             if grp is None:
-                grp = prepared.trunk_group(self)
-                self.__dict__["_hdmoe_trunk_group"] = grp
+                grp = prepared.trunk_group(self, router_convs=not tc_trunk)
+                self.__dict__[key] = grp
             with grp.prepared(self.training):
                 return self._forward_body(x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point,
                                           softness, alpha_routing, noise)
         return self._forward_body(x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point,
                                   softness, alpha_routing, noise)
+
+    def _router_trunk(self, x):
+        """The grouped tcgen05 trunk runner of the two routers, or None when the configuration does not use it (fp32
+        expert path, CPU tensors, unsupported shapes, switched off)."""
+        from . import router_trunk as rt
+        if not (x.is_cuda and rt.enabled() and get_expert_dtype() == torch.bfloat16):
+            return None
+        routers = [self.vit_router, self.Unet_router]
+        if not rt.GroupedRouterTrunk.supported(routers, x):
+            return None
+        runner = self.__dict__.get("_hdmoe_router_trunk")
+        if runner is None:
+            runner = rt.GroupedRouterTrunk(routers)
+            self.__dict__["_hdmoe_router_trunk"] = runner
+        return runner
 
     def _forward_body(self, x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point, softness,
                       alpha_routing, noise):
@@ -299,23 +316,28 @@ class HDMOEM(nn.Module):
             s_unet = scaling[:, 1:2].view(-1, 1, 1, 1)
         in_unet = s_unet * feats
         in_vit = s_vit * feats
+        # router trunks of both routers as grouped tcgen05 launches (bf16 configuration): pooled features up front
+        trunk = self._router_trunk(x)
+        pool_vit = pool_un = None
+        if trunk is not None:
+            pool_vit, pool_un = trunk([in_vit, in_unet], self.training)
         # the ViT router is evaluated first (RNG order, quirk Q2)
         if _BRANCH_STREAMS[0] and x.is_cuda and _EP["placement"] is None:
             # ViT branch (router + MoE layer) beside the U-Net branch; host program order as in the reference
-            with _fork(_streams(x.device, "branch", 1)[0], (in_vit, te, text_emb, Vit_router_mask)) as fk:
+            with _fork(_streams(x.device, "branch", 1)[0], (in_vit, te, text_emb, Vit_router_mask, pool_vit)) as fk:
                 w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
-                                                        noise=noise.get("vit"))
+                                                        noise=noise.get("vit"), pooled=pool_vit)
             w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
-                                                  noise=noise.get("unet"))
+                                                  noise=noise.get("unet"), pooled=pool_un)
             out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k)
             with torch.cuda.stream(fk.s):
                 out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k)
             fk.join(w_vit, p_vit, raw_vit, out_v)
         else:
             w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
-                                                    noise=noise.get("vit"))
+                                                    noise=noise.get("vit"), pooled=pool_vit)
             w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
-                                                  noise=noise.get("unet"))
+                                                  noise=noise.get("unet"), pooled=pool_un)
             out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k)
             out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k)
         uf = out_u.flatten(2).transpose(1, 2)

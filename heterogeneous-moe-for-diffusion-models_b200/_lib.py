@@ -67,6 +67,8 @@ PROTOTYPES = {
     "hdmoe_vit_block_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "hdmoe_gn1_relu_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "hdmoe_gn1_relu_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "hdmoe_gn1_relu_fwd_t": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _f, _i, _p]),
+    "hdmoe_gn1_relu_bwd_t": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "hdmoe_attn_d4_tc_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "hdmoe_attn_d4_tc_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "hdmoe_wprep_fwd_resident": (_i, [_p, _i, _i, _i, _p]),

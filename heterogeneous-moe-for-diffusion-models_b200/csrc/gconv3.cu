@@ -22,6 +22,15 @@
 
 namespace hdmoe {
 
+#ifdef HDMOE_G3_TRACE
+__device__ long long g3_trace[148 * 64];
+__device__ __forceinline__ long long g3_gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define G3T(slot) do { if (blockIdx.x < 148 && tcount < 8 && lane == 0) { g3_trace[blockIdx.x * 64 + tcount * 8 + (slot)] = clock64(); \
+    if ((slot) == 0) g3_trace[blockIdx.x * 64 + tcount * 8 + 6] = g3_gtime(); if ((slot) == 5) g3_trace[blockIdx.x * 64 + tcount * 8 + 7] = g3_gtime(); } } while (0)
+#else
+#define G3T(slot) do { } while (0)
+#endif
+
 constexpr int kG3Issuers = 2;      // one per M-tile accumulator (N = 128 MMAs take 64 cycles; one thread issues one per ~103)
 constexpr int kG3Threads = 32 * (1 + kG3Issuers + 4);
 constexpr int kG3MaxE = HDMOE_MAX_EXPERTS;
@@ -328,55 +337,75 @@ gconv3_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
         }
     } else if (warp <= kG3Issuers) {
         // ============================== MMA issuers (warp w owns M-tile w-1) ==============================
+        // The WHOLE warp runs this loop converged and one elected lane issues: tile geometry is made warp-uniform with
+        // redux, so descriptors / barrier addresses stay in uniform registers (a loop entered by a single lane makes
+        // the compiler wrap every UTCHMMA in an ELECT + R2UR waterfall: ~100 cycles per MMA per issuing thread).
         constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
         const int mt = warp - 1;
-        int as = 0, bs = 0, acc = 0;
+        int as = 0, bs = 0, acc = 0, tcount = 0;
+        (void)tcount;
         uint32_t aph = 0, bph = 0, acc_ph = 0;
-        for (; lane == 0;) {
-            const int i = next_tile(false);
+        for (;;) {
+            const int i = uni(next_tile(true));
             if (i < 0) break;
             G3Tile t;
-            if (!tile_at(i, t)) continue;
-            const int k = p.ksize[t.kc], Wp = p.wp[t.kc], G = (k + TPM - 1) / TPM;
-            const bool active = mt < t.mt_n;
+            const bool ok = tile_at(i, t);
+            if (!uni((int)ok)) continue;
+            const int k = uni(p.ksize[t.kc]), Wp = uni(p.wp[t.kc]), G = (k + TPM - 1) / TPM;
+            const int c0u = uni(t.c0);
+            const bool active = uni((int)(mt < t.mt_n)) != 0;
+            if (mt == 0) G3T(0);
             mb_wait(&t_empty[acc], acc_ph ^ 1);
             tc_fence_after();
+            if (mt == 0) G3T(1);
             const uint32_t d = tmem_base + (uint32_t)((acc * kG3Issuers + mt) * 128);
             for (int c = 0; c < p.upt; ++c) {
                 mb_wait(&a_full[as], aph);
                 tc_fence_after();
+                if (mt == 0 && c == 0) G3T(2);
                 const uint64_t a_desc0 =
-                    umma_desc<KC>(s2u(a_buf + (size_t)as * p.a_stage_bytes) + (uint32_t)(t.c0 + mt * MS) * ROWB);
+                    umma_desc<KC>(s2u(a_buf + (size_t)as * p.a_stage_bytes) + (uint32_t)(c0u + mt * MS) * ROWB);
                 for (int tr = 0; tr < k; ++tr)
                     for (int g = 0; g < G; ++g) {
                         mb_wait(&b_full[bs], bph);
-                        if (active) {
-                            tc_fence_after();
-                            const int ntaps = (k - g * TPM) < TPM ? (k - g * TPM) : TPM;
-                            const uint32_t idesc = idesc0 | ((uint32_t)((ntaps * COUT) >> 3) << 17);
-                            const uint64_t bd = umma_desc<KC>(s2u(b_buf + (size_t)bs * B_STAGE));
-                            const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(tr * Wp + g * TPM) * ROWB) >> 4);
+                        tc_fence_after();
+                        const int ntaps = (k - g * TPM) < TPM ? (k - g * TPM) : TPM;
+                        const uint32_t idesc = idesc0 | ((uint32_t)((ntaps * COUT) >> 3) << 17);
+                        const uint64_t bd = umma_desc<KC>(s2u(b_buf + (size_t)bs * B_STAGE));
+                        const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(tr * Wp + g * TPM) * ROWB) >> 4);
+                        const uint32_t first = (uint32_t)(c | tr | g);
+                        if (elect_one()) {
+                            if (active) {
 #pragma unroll
-                            for (int kk = 0; kk < KC / 16; ++kk)
-                                tc_mma(d, ad + 2 * kk, bd + 2 * kk, idesc, (c | tr | g | kk) != 0);
-                            tc_commit(&b_empty[bs]);
-                        } else {
-                            mb_arrive(&b_empty[bs]);
+                                for (int kk = 0; kk < KC / 16; ++kk) tc_mma(d, ad + 2 * kk, bd + 2 * kk, idesc, first | kk);
+                                tc_commit(&b_empty[bs]);
+                            } else {
+                                mb_arrive(&b_empty[bs]);
+                            }
                         }
+                        __syncwarp();
                         if (++bs == kG3BStages) {
                             bs = 0;
                             bph ^= 1;
                         }
                     }
-                if (active) tc_commit(&a_empty[as]);
-                else mb_arrive(&a_empty[as]);
+                if (elect_one()) {
+                    if (active) tc_commit(&a_empty[as]);
+                    else mb_arrive(&a_empty[as]);
+                }
+                __syncwarp();
                 if (++as == kG3AStages) {
                     as = 0;
                     aph ^= 1;
                 }
             }
-            if (active) tc_commit(&t_full[acc]);
-            else mb_arrive(&t_full[acc]);
+            if (elect_one()) {
+                if (active) tc_commit(&t_full[acc]);
+                else mb_arrive(&t_full[acc]);
+            }
+            __syncwarp();
+            if (mt == 0) G3T(3);
+            ++tcount;
             if (++acc == 2) {
                 acc = 0;
                 acc_ph ^= 1;
@@ -385,7 +414,8 @@ gconv3_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
     } else {
         // ============================== epilogue (4 warps): TMEM -> shift-add -> registers -> global ==============
         const int quad = warp & 3;
-        int acc = 0, mcount = 0;
+        int acc = 0, mcount = 0, tcount = 0;
+        (void)tcount;
         uint32_t acc_ph = 0;
         for (;;) {
             const int i = next_tile(true);
@@ -404,6 +434,7 @@ gconv3_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
             }
             mb_wait(&t_full[acc], acc_ph);
             tc_fence_after();
+            if (quad == 0) G3T(4);
             const int fl = (p.scale ? 1 : 0) | (p.act == 1 ? 2 : 0) | (p.res ? 4 : 0);
             const uint32_t tacc = tmem_base + (uint32_t)(acc * kG3Issuers * 128);
             switch (fl) {
@@ -418,6 +449,8 @@ gconv3_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
+            if (quad == 0) G3T(5);
+            ++tcount;
             if (lane == 0) mb_arrive(&t_empty[acc]);
             if (++acc == 2) {
                 acc = 0;
@@ -455,6 +488,12 @@ static int launch_gconv3(const CUtensorMap* ta, const CUtensorMap& tb, const GCo
 
 }  // namespace hdmoe
 using namespace hdmoe;
+
+#ifdef HDMOE_G3_TRACE
+extern "C" int hdmoe_g3_trace_read(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g3_trace, sizeof(long long) * 148 * 64);
+}
+#endif
 
 extern "C" int hdmoe_gconv3_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H, int W, int Cin_pad,
                                 int Cout, int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev,

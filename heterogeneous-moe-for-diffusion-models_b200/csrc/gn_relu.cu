@@ -1,5 +1,6 @@
 // Router trunk normalisation (Router.hard_route, models/model_components.py:92-103): GroupNorm(1, C) + ReLU, and
-// for the last layer + AdaptiveAvgPool2d((1,1)), on channels-last fp32 activations [B, HW, C].
+// for the last layer + AdaptiveAvgPool2d((1,1)), on channels-last activations [B, HW, C], fp32 (library-convolution trunk)
+// or bf16 (tcgen05 trunk: the activations between the grouped convolutions; statistics and the pooled output stay fp32).
 //
 // The library path costs ~5 tensor passes forward and ~11 backward per layer (moments, unvectorised broadcast
 // affine, ReLU, their backward reductions) plus NCHW<->NHWC conversions around every convolution.  GroupNorm with
@@ -25,18 +26,20 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
 }
 
 // y may be NULL (pooled-only); pooled may be NULL.  stats[b] = (mean, rstd).
+template <typename T>
 __global__ void __launch_bounds__(kGnThreads)
-gn1_relu_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gamma, const float4* __restrict__ beta,
-                    float4* __restrict__ y, float* __restrict__ pooled, float2* __restrict__ stats, int HW, int C, float eps) {
+gn1_relu_fwd_kernel(const T* __restrict__ x, const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                    T* __restrict__ y, float* __restrict__ pooled, float2* __restrict__ stats, int HW, int C, float eps,
+                    int rpg) {
     __shared__ double red[32];
     __shared__ float4 pr[kGnThreads];
     const int b = blockIdx.x, cq = C >> 2;
     const long long nvec = (long long)HW * cq;
-    const float4* xs = x + (size_t)b * nvec;
+    const T* xs = x + (size_t)b * nvec * 4;
     float s = 0.f, ss = 0.f;
 #pragma unroll 4
     for (long long i = threadIdx.x; i < nvec; i += kGnThreads) {
-        const float4 v = xs[i];
+        const float4 v = Vec4<T>::load(xs + 4 * i);
         s += (v.x + v.y) + (v.z + v.w);
         ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
     }
@@ -46,20 +49,21 @@ gn1_relu_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gam
     const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
     if (threadIdx.x == 0) stats[b] = make_float2(mu, rstd);
     const int c4 = threadIdx.x % cq;                       // kGnThreads % cq == 0 (host check): fixed channel quad
-    const float4 g = gamma[c4], be = beta[c4];
+    const int grp = b / rpg;                               // rows [grp * rpg, +rpg) share one (gamma, beta): one router each
+    const float4 g = gamma[grp * cq + c4], be = beta[grp * cq + c4];
     const float4 a = make_float4(rstd * g.x, rstd * g.y, rstd * g.z, rstd * g.w);
     const float4 sh = make_float4(be.x - mu * a.x, be.y - mu * a.y, be.z - mu * a.z, be.w - mu * a.w);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4* ys = y ? y + (size_t)b * nvec : nullptr;
+    T* ys = y ? y + (size_t)b * nvec * 4 : nullptr;
 #pragma unroll 4
     for (long long i = threadIdx.x; i < nvec; i += kGnThreads) {
-        const float4 v = xs[i];
+        const float4 v = Vec4<T>::load(xs + 4 * i);
         float4 r;
         r.x = fmaxf(fmaf(v.x, a.x, sh.x), 0.f);
         r.y = fmaxf(fmaf(v.y, a.y, sh.y), 0.f);
         r.z = fmaxf(fmaf(v.z, a.z, sh.z), 0.f);
         r.w = fmaxf(fmaf(v.w, a.w, sh.w), 0.f);
-        if (ys) ys[i] = r;
+        if (ys) Vec4<T>::store(ys + 4 * i, r);
         acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
     }
     if (pooled) {
@@ -78,20 +82,23 @@ gn1_relu_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gam
 }
 
 // dy (activation gradient) or dpooled (gradient of the pooled output, broadcast / HW) -- exactly one is non-NULL
+template <typename T>
 __global__ void __launch_bounds__(kGnThreads)
-gn1_relu_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gamma, const float4* __restrict__ beta,
-                    const float2* __restrict__ stats, const float4* __restrict__ dy, const float* __restrict__ dpooled,
-                    float4* __restrict__ dx, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int HW, int C) {
+gn1_relu_bwd_kernel(const T* __restrict__ x, const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                    const float2* __restrict__ stats, const T* __restrict__ dy, const float* __restrict__ dpooled,
+                    T* __restrict__ dx, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int HW, int C,
+                    int rpg) {
     __shared__ double red[32];
     __shared__ float4 pr[kGnThreads];
     const int b = blockIdx.x, cq = C >> 2;
     const long long nvec = (long long)HW * cq;
-    const float4* xs = x + (size_t)b * nvec;
-    const float4* gs = dy ? dy + (size_t)b * nvec : nullptr;
+    const T* xs = x + (size_t)b * nvec * 4;
+    const T* gs = dy ? dy + (size_t)b * nvec * 4 : nullptr;
     const float2 st = stats[b];
     const float mu = st.x, rstd = st.y;
     const int c4 = threadIdx.x % cq;
-    const float4 g = gamma[c4], be = beta[c4];
+    const int grp = b / rpg;
+    const float4 g = gamma[grp * cq + c4], be = beta[grp * cq + c4];
     float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (dpooled) {
         gp = reinterpret_cast<const float4*>(dpooled + (size_t)b * C)[c4];
@@ -112,8 +119,8 @@ gn1_relu_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gam
     }
 #pragma unroll 4
     for (long long i = threadIdx.x; i < nvec; i += kGnThreads) {
-        const float4 v = xs[i];
-        const float4 gi = gs ? gs[i] : gp;
+        const float4 v = Vec4<T>::load(xs + 4 * i);
+        const float4 gi = gs ? Vec4<T>::load(gs + 4 * i) : gp;
         float t;
         GN_ELEM(v.x, gi.x, g.x, be.x, t, dg.x, db.x)
         GN_ELEM(v.y, gi.y, g.y, be.y, t, dg.y, db.y)
@@ -146,11 +153,11 @@ gn1_relu_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gam
         }
         reinterpret_cast<float4*>(dbeta_part + (size_t)b * C)[threadIdx.x] = t;
     }
-    float4* ds = dx + (size_t)b * nvec;
+    T* ds = dx + (size_t)b * nvec * 4;
 #pragma unroll 4
     for (long long i = threadIdx.x; i < nvec; i += kGnThreads) {
-        const float4 v = xs[i];
-        const float4 gi = gs ? gs[i] : gp;
+        const float4 v = Vec4<T>::load(xs + 4 * i);
+        const float4 gi = gs ? Vec4<T>::load(gs + 4 * i) : gp;
         float4 r;
 #define GN_DX(X, G, GA, BE, R)                                   \
     {                                                            \
@@ -163,7 +170,7 @@ gn1_relu_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gam
         GN_DX(v.z, gi.z, g.z, be.z, r.z)
         GN_DX(v.w, gi.w, g.w, be.w, r.w)
 #undef GN_DX
-        ds[i] = r;
+        Vec4<T>::store(ds + 4 * i, r);
     }
 }
 
@@ -172,25 +179,51 @@ using namespace hdmoe;
 
 static bool gn_shape_ok(int C) { return C >= 4 && C % 4 == 0 && kGnThreads % (C / 4) == 0; }
 
-extern "C" int hdmoe_gn1_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* pooled, float* stats,
-                                  int B, int HW, int C, float eps, hdmoe_stream_t stream) {
+extern "C" int hdmoe_gn1_relu_fwd_t(const void* x, int dtype, const float* gamma, const float* beta, void* y, float* pooled,
+                                    float* stats, int B, int HW, int C, float eps, int rows_per_group,
+                                    hdmoe_stream_t stream) {
+    const int rpg = rows_per_group > 0 ? rows_per_group : B;
     HDMOE_CHECK_ARG(x && gamma && beta && stats && (y || pooled) && B >= 1 && HW >= 1, "gn1_relu_fwd: bad args");
     HDMOE_CHECK_ARG(gn_shape_ok(C), "gn1_relu_fwd: C / 4 must divide 1024 (got C = %d)", C);
-    gn1_relu_fwd_kernel<<<B, kGnThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)gamma, (const float4*)beta,
-                                                                    (float4*)y, pooled, (float2*)stats, HW, C, eps);
+    HDMOE_CHECK_ARG(dtype == HDMOE_F32 || dtype == HDMOE_BF16, "gn1_relu_fwd: dtype must be f32 or bf16");
+    if (dtype == HDMOE_F32)
+        gn1_relu_fwd_kernel<float><<<B, kGnThreads, 0, (cudaStream_t)stream>>>(
+            (const float*)x, (const float4*)gamma, (const float4*)beta, (float*)y, pooled, (float2*)stats, HW, C, eps, rpg);
+    else
+        gn1_relu_fwd_kernel<__nv_bfloat16><<<B, kGnThreads, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, (const float4*)gamma, (const float4*)beta, (__nv_bfloat16*)y, pooled, (float2*)stats, HW,
+            C, eps, rpg);
     HDMOE_CHECK_LAUNCH();
     return HDMOE_OK;
+}
+
+extern "C" int hdmoe_gn1_relu_bwd_t(const void* x, int dtype, const float* gamma, const float* beta, const float* stats,
+                                    const void* dy, const float* dpooled, void* dx, float* dgamma_part, float* dbeta_part,
+                                    int B, int HW, int C, int rows_per_group, hdmoe_stream_t stream) {
+    const int rpg = rows_per_group > 0 ? rows_per_group : B;
+    HDMOE_CHECK_ARG(x && gamma && beta && stats && dx && dgamma_part && dbeta_part && B >= 1 && HW >= 1, "gn1_relu_bwd: bad args");
+    HDMOE_CHECK_ARG((dy != nullptr) != (dpooled != nullptr), "gn1_relu_bwd: exactly one of dy / dpooled");
+    HDMOE_CHECK_ARG(gn_shape_ok(C), "gn1_relu_bwd: C / 4 must divide 1024 (got C = %d)", C);
+    HDMOE_CHECK_ARG(dtype == HDMOE_F32 || dtype == HDMOE_BF16, "gn1_relu_bwd: dtype must be f32 or bf16");
+    if (dtype == HDMOE_F32)
+        gn1_relu_bwd_kernel<float><<<B, kGnThreads, 0, (cudaStream_t)stream>>>(
+            (const float*)x, (const float4*)gamma, (const float4*)beta, (const float2*)stats, (const float*)dy, dpooled,
+            (float*)dx, dgamma_part, dbeta_part, HW, C, rpg);
+    else
+        gn1_relu_bwd_kernel<__nv_bfloat16><<<B, kGnThreads, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, (const float4*)gamma, (const float4*)beta, (const float2*)stats,
+            (const __nv_bfloat16*)dy, dpooled, (__nv_bfloat16*)dx, dgamma_part, dbeta_part, HW, C, rpg);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_gn1_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* pooled, float* stats,
+                                  int B, int HW, int C, float eps, hdmoe_stream_t stream) {
+    return hdmoe_gn1_relu_fwd_t(x, HDMOE_F32, gamma, beta, y, pooled, stats, B, HW, C, eps, 0, stream);
 }
 
 extern "C" int hdmoe_gn1_relu_bwd(const float* x, const float* gamma, const float* beta, const float* stats, const float* dy,
                                   const float* dpooled, float* dx, float* dgamma_part, float* dbeta_part, int B, int HW, int C,
                                   hdmoe_stream_t stream) {
-    HDMOE_CHECK_ARG(x && gamma && beta && stats && dx && dgamma_part && dbeta_part && B >= 1 && HW >= 1, "gn1_relu_bwd: bad args");
-    HDMOE_CHECK_ARG((dy != nullptr) != (dpooled != nullptr), "gn1_relu_bwd: exactly one of dy / dpooled");
-    HDMOE_CHECK_ARG(gn_shape_ok(C), "gn1_relu_bwd: C / 4 must divide 1024 (got C = %d)", C);
-    gn1_relu_bwd_kernel<<<B, kGnThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)gamma, (const float4*)beta,
-                                                                    (const float2*)stats, (const float4*)dy, dpooled, (float4*)dx,
-                                                                    dgamma_part, dbeta_part, HW, C);
-    HDMOE_CHECK_LAUNCH();
-    return HDMOE_OK;
+    return hdmoe_gn1_relu_bwd_t(x, HDMOE_F32, gamma, beta, stats, dy, dpooled, dx, dgamma_part, dbeta_part, B, HW, C, 0, stream);
 }

@@ -58,6 +58,7 @@ struct WGrad2Params {
     int n_experts;
     int a_stage_bytes, b_stage_bytes;  // a_stage_bytes includes the lead-in
     int upg;                           // units (TPM consecutive taps of one kernel row) per tap group
+    int cout_total, o_off;             // dY / dW channel count and this launch's first output channel (Cout = 128: 2 passes)
     const int32_t* row_expert;
     const int32_t* n_rows_dev;
     float* dW;                         // fp32 [w_rows_total][cin_pad], tap-major blocks per expert (accumulated)
@@ -286,7 +287,7 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                      for (int u = u_lo; u < u_hi; ++u) {
                          const int tr = u / upr, s0 = (u - tr * upr) * TPM;
                          const int ts = s0 + TPM - 1 - a;               // this lane's tap (may lie past the kernel row)
-                         float* drow = p.dW + ((size_t)p.wrow[e] + (size_t)(tr * k + ts) * COUT + o) * p.cin_pad;
+                         float* drow = p.dW + ((size_t)p.wrow[e] + (size_t)(tr * k + ts) * p.cout_total + p.o_off + o) * p.cin_pad;
                          for (int c = 0; c < p.nchunks; ++c) {
 #pragma unroll 1
                              for (int c0 = 0; c0 < KC; c0 += 32) {
@@ -348,11 +349,35 @@ extern "C" int hdmoe_wg_trace_read(long long* host_out) {
 }
 #endif
 
+// one pass over output channels [o_off, o_off + Cout) of a dY / dW that hold cout_total channels
+static int gconv_wgrad_pass(const void* X, const void* dY, float* dW, int cap_rows, int H, int W, int Cin_pad, int Cout,
+                            int cout_total, int o_off, int64_t w_rows_total, const int32_t* row_expert,
+                            const int32_t* n_rows_dev, int n_experts, const int32_t* ksize_host, const int32_t* wrow_host,
+                            hdmoe_stream_t stream);
+
 extern "C" int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int cap_rows, int H, int W, int Cin_pad,
                                  int Cout, int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev,
                                  int n_experts, const int32_t* ksize_host, const int32_t* wrow_host,
                                  hdmoe_stream_t stream) {
-    HDMOE_CHECK_ARG(X && dY && dW && row_expert && n_rows_dev && ksize_host && wrow_host, "gconv_wgrad: null pointer");
+    HDMOE_CHECK_ARG(Cout == 32 || Cout == 64 || Cout == 128, "gconv_wgrad: Cout must be 32, 64 or 128 (got %d)", Cout);
+    if (Cout == 128) {     // the router-trunk widths: two 64-channel passes over the same input windows
+        for (int h = 0; h < 2; ++h) {
+            const int rc = gconv_wgrad_pass(X, dY, dW, cap_rows, H, W, Cin_pad, 64, 128, 64 * h, w_rows_total, row_expert,
+                                            n_rows_dev, n_experts, ksize_host, wrow_host, stream);
+            if (rc != HDMOE_OK) return rc;
+        }
+        return HDMOE_OK;
+    }
+    return gconv_wgrad_pass(X, dY, dW, cap_rows, H, W, Cin_pad, Cout, Cout, 0, w_rows_total, row_expert, n_rows_dev,
+                            n_experts, ksize_host, wrow_host, stream);
+}
+
+static int gconv_wgrad_pass(const void* X, const void* dY_base, float* dW, int cap_rows, int H, int W, int Cin_pad, int Cout,
+                            int cout_total, int o_off, int64_t w_rows_total, const int32_t* row_expert,
+                            const int32_t* n_rows_dev, int n_experts, const int32_t* ksize_host, const int32_t* wrow_host,
+                            hdmoe_stream_t stream) {
+    const void* dY = (const void*)((const __nv_bfloat16*)dY_base + o_off);
+    HDMOE_CHECK_ARG(X && dY_base && dW && row_expert && n_rows_dev && ksize_host && wrow_host, "gconv_wgrad: null pointer");
     HDMOE_CHECK_ARG(n_experts >= 1 && n_experts <= kW2MaxE, "gconv_wgrad: 1 <= n_experts <= %d", kW2MaxE);
     HDMOE_CHECK_ARG(Cout == 32 || Cout == 64, "gconv_wgrad: Cout must be 32 or 64 (got %d)", Cout);
     HDMOE_CHECK_ARG(Cin_pad >= 32 && Cin_pad % 32 == 0 && Cin_pad <= 256, "gconv_wgrad: Cin_pad in 32..256, multiple of 32");
@@ -375,6 +400,8 @@ extern "C" int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int c
     p.row_expert = row_expert;
     p.n_rows_dev = n_rows_dev;
     p.dW = dW;
+    p.cout_total = cout_total;
+    p.o_off = o_off;
     int ncls = 0, cls_k[kW2Classes], kmax = 1;
     for (int e = 0; e < n_experts; ++e) {
         const int k = ksize_host[e];
@@ -454,7 +481,8 @@ extern "C" int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int c
         cuuint32_t es[4] = {1, 1, 1, 1};
         {
             cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)cap_rows};
-            cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+            cuuint64_t strides[3] = {(cuuint64_t)cout_total * 2, (cuuint64_t)W * cout_total * 2,
+                                     (cuuint64_t)H * W * cout_total * 2};
             cuuint32_t box[4] = {(cuuint32_t)Cout, (cuuint32_t)Wp, (cuuint32_t)SH, 1};
             CUresult r = enc(&ta[c], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dY), dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, swa, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

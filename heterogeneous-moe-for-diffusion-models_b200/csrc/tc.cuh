@@ -72,6 +72,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     constexpr uint64_t layout = KC == 64 ? 2 : 4;                // SWIZZLE_128B : SWIZZLE_64B
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
+// one lane of a CONVERGED warp (the issuing thread of tcgen05.mma / commit); everything the elected lane consumes should
+// be computed by the whole warp outside the elected region so that it lives in uniform registers
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// warp-uniform copy of a value every lane holds (redux writes a uniform register: the compiler can then keep address /
+// descriptor arithmetic on the uniform datapath instead of a per-instruction R2UR waterfall)
+__device__ __forceinline__ int uni(int v) { return __reduce_max_sync(0xffffffffu, v); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

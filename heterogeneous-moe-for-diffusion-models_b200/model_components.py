@@ -101,9 +101,14 @@ class Router(nn.Module):
         return seq[10](h.view(B, Cn, 1, 1)).reshape(B, Cn)
 
     def forward(self, x: torch.Tensor, time_emb: torch.Tensor, mask: Optional[torch.Tensor] = None,
-                zeta: Optional[float] = 1e-2, noise: Optional[torch.Tensor] = None):
+                zeta: Optional[float] = 1e-2, noise: Optional[torch.Tensor] = None,
+                pooled: Optional[torch.Tensor] = None):
+        """`pooled` (B200 extra): the trunk's pooled features when they were computed outside (router_trunk.py runs the
+        trunks of both routers as grouped tcgen05 launches); only the Dropout of hard_route is applied to them here."""
         B = x.shape[0]
-        if x.is_cuda and x.dtype == torch.float32 and _FUSED_TRUNK[0] and self._fusable():
+        if pooled is not None:
+            pooled = self.hard_route[10](pooled.reshape(B, -1, 1, 1)).reshape(B, -1).float()
+        elif x.is_cuda and x.dtype == torch.float32 and _FUSED_TRUNK[0] and self._fusable():
             pooled = self._fused_trunk(x).float()
         else:
             if x.is_cuda and _CHANNELS_LAST[0]:

@@ -623,6 +623,52 @@ def gn1_relu(x, gamma, beta, eps: float = 1e-5, pool: bool = False):
     return _GN1Relu.apply(x, gamma, beta, eps, pool)
 
 
+class _GN1ReluNHWC(torch.autograd.Function):
+    """relu(group_norm(x, 1 group)) [+ mean over H, W] on NHWC bf16 rows x [R, H, W, C]: the activations between the
+    tcgen05 router-trunk convolutions (csrc/gn_relu.cu, bf16 instantiation; statistics, pooled output and the
+    gamma / beta gradients in fp32).  gamma / beta are [G, C]: rows [g * R / G, (g + 1) * R / G) use table row g (the
+    trunks of several routers run as one grouped launch)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, pool):
+        _cuda(x, gamma, beta)
+        if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.ndim != 4:
+            raise RuntimeError("gn1_relu_nhwc: x must be contiguous bfloat16 [R, H, W, C]")
+        R, H, W, Cn = x.shape
+        gamma, beta = _f32c(gamma).reshape(-1, Cn), _f32c(beta).reshape(-1, Cn)
+        G = gamma.shape[0]
+        if R % G != 0 or beta.shape[0] != G:
+            raise RuntimeError("gn1_relu_nhwc: rows must split evenly over the gamma / beta groups")
+        stats = torch.empty(R, 2, dtype=torch.float32, device=x.device)
+        y = None if pool else torch.empty_like(x)
+        pooled = torch.empty(R, Cn, dtype=torch.float32, device=x.device) if pool else None
+        L.check(L.lib().hdmoe_gn1_relu_fwd_t(_p(x), L.BF16, _p(gamma), _p(beta), _p(y), _p(pooled), _p(stats), R, H * W, Cn,
+                                             float(eps), R // G, _st()), "gn1_relu_fwd_t")
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.pool, ctx.G = pool, G
+        return pooled if pool else y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, beta, stats = ctx.saved_tensors
+        R, H, W, Cn = x.shape
+        G = ctx.G
+        g = g.float().contiguous() if ctx.pool else g.to(torch.bfloat16).contiguous()
+        dx = torch.empty_like(x)
+        parts = torch.empty(2, R, Cn, dtype=torch.float32, device=x.device)
+        L.check(L.lib().hdmoe_gn1_relu_bwd_t(_p(x), L.BF16, _p(gamma), _p(beta), _p(stats), None if ctx.pool else _p(g),
+                                             _p(g) if ctx.pool else None, _p(dx), _p(parts[0]), _p(parts[1]), R, H * W, Cn,
+                                             R // G, _st()), "gn1_relu_bwd_t")
+        sums = parts.view(2, G, R // G, Cn).sum(dim=2)
+        return dx, sums[0], sums[1], None, None
+
+
+def gn1_relu_nhwc(x, gamma, beta, eps: float = 1e-5, pool: bool = False):
+    """ReLU(GroupNorm(1, C)(x)) for NHWC bf16 rows [R, H, W, C] with [G, C] (or [C]) affine tables; pool=True returns
+    the fp32 [R, C] spatial mean."""
+    return _GN1ReluNHWC.apply(x, gamma, beta, eps, pool)
+
+
 def gn1_relu_supported(channels: int) -> bool:
     return channels % 4 == 0 and 1024 % (channels // 4) == 0
 

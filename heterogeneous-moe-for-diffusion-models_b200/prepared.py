@@ -201,13 +201,16 @@ def vit_expert_group(experts, out_dtype) -> PreparedGroup:
     return PreparedGroup(mods, gains, owner, len(experts), out_dtype)
 
 
-def trunk_group(net) -> PreparedGroup:
-    """The always-active MP_Conv modules of HDMOEM outside the experts (gain 1 everywhere)."""
+def trunk_group(net, router_convs: bool = True) -> PreparedGroup:
+    """The always-active MP_Conv modules of HDMOEM outside the experts (gain 1 everywhere).  router_convs=False leaves
+    out the routers' trunk convolutions (router_trunk.py prepares them itself as tcgen05 operands)."""
     mods = [net.input_proj, net.out_fourier1, net.out_fourier2]
     if hasattr(net, "scaling_net"):
         mods += [net.scaling_net.soft_route[0], net.scaling_net.soft_route[3], net.scaling_net.linear]
     for r in (net.vit_router, net.Unet_router):
-        mods += [r.hard_route[0], r.hard_route[3], r.hard_route[6], r.time_linear, r.linear]
+        if router_convs:
+            mods += [r.hard_route[0], r.hard_route[3], r.hard_route[6]]
+        mods += [r.time_linear, r.linear]
     for a in (net.cross_attn, net.cross_attn_text):
         mods += [a.q_proj, a.k_proj, a.v_proj, a.out_proj]
     mods += [net.gate1, net.gate2, net.output_proj]

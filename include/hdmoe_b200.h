@@ -263,6 +263,15 @@ int hdmoe_gn1_relu_fwd(const float* x, const float* gamma, const float* beta, fl
 int hdmoe_gn1_relu_bwd(const float* x, const float* gamma, const float* beta, const float* stats, const float* dy,
                        const float* dpooled, float* dx, float* dgamma_part, float* dbeta_part, int B, int HW, int C,
                        hdmoe_stream_t stream);
+/* Same operation with the activation tensors (x, y, dy, dx) in `dtype` (HDMOE_F32 or HDMOE_BF16; NHWC bf16 is the layout
+ * between the tcgen05 router-trunk convolutions); gamma, beta, stats, pooled and the partials stay fp32.  Rows
+ * [g * rows_per_group, (g + 1) * rows_per_group) use gamma[g], beta[g] ([G, C] tables: several routers in one launch);
+ * rows_per_group <= 0 means one group. */
+int hdmoe_gn1_relu_fwd_t(const void* x, int dtype, const float* gamma, const float* beta, void* y, float* pooled,
+                         float* stats, int B, int HW, int C, float eps, int rows_per_group, hdmoe_stream_t stream);
+int hdmoe_gn1_relu_bwd_t(const void* x, int dtype, const float* gamma, const float* beta, const float* stats,
+                         const void* dy, const float* dpooled, void* dx, float* dgamma_part, float* dbeta_part, int B,
+                         int HW, int C, int rows_per_group, hdmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (8) Fused NHWC bf16 elementwise kernels of the U-Net expert block -- replace the elementwise ATen chains of

@@ -46,7 +46,7 @@ int hdmoe_gconv3_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H
  *   dW[wrow[e] + tap*Cout + o, c] += sum over rows r of expert e and pixels q of dY[r,q,o] * Xpad[r, q+delta_tap, c]
  * dW is fp32 [w_rows_total, Cin_pad] in the tap-major block layout of the forward operand and must be zeroed by
  * the caller before the first accumulation of a step.  X / dY are NHWC bf16 as in hdmoe_gconv2_fwd.
- * Constraints: Cout in {32, 64}; Cin_pad % 32 == 0, <= 256; H % 4 == 0 (the largest of 32 / 16 / 8 / 4 strip rows that
+ * Constraints: Cout in {32, 64, 128} (128 runs as two 64-channel passes); Cin_pad % 32 == 0, <= 256; H % 4 == 0 (the largest of 32 / 16 / 8 / 4 strip rows that
  * divides H and fits shared memory is used); W <= 232.  Same stream rule as hdmoe_gconv2_fwd. */
 int hdmoe_gconv_wgrad(const void* X, const void* dY, float* dW, int cap_rows, int H, int W, int Cin_pad, int Cout,
                       int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev, int n_experts,

@@ -1,10 +1,11 @@
 import ctypes as C, sys, torch, numpy as np
 import os
-lib = C.CDLL(os.environ.get("G2LIB", "tools/libg2trace.so"))
+VER = os.environ.get("GVER", "2")
+lib = C.CDLL(os.environ.get("G2LIB", "tools/libg%strace.so" % VER))
 dev = "cuda"
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 counts, ks = [36, 48, 75, 97], [3, 3, 5, 5]
-R = sum(counts); Cin = 64; Cout = 64
+R = sum(counts); Cin = int(os.environ.get('CIN', 64)); Cout = int(os.environ.get('COUT', 64))
 row_e = sum(([e] * c for e, c in enumerate(counts)), [])
 re_d = torch.tensor(row_e, dtype=torch.int32, device=dev); nr_d = torch.tensor([R], dtype=torch.int32, device=dev)
 p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
@@ -15,7 +16,7 @@ for k in ks:
 wt = (torch.randn(tot, Cin, device=dev) / 30).to(torch.bfloat16)
 y = torch.empty(R, H, H, Cout, dtype=torch.bfloat16, device=dev)
 ks_h = (C.c_int32 * 4)(*ks); wr_h = (C.c_int32 * 4)(*wrow)
-fn = lib.hdmoe_gconv2_fwd
+fn = getattr(lib, 'hdmoe_gconv%s_fwd' % VER)
 fn.restype = C.c_int
 fn.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
 for _ in range(3):
@@ -27,10 +28,11 @@ ev[0].record()
 for _ in range(10):
     fn(p(x), p(wt), p(y), R, H, H, Cin, Cout, tot, p(re_d), p(nr_d), 4, ks_h, wr_h, None, 0, None, 0.0, 0.0, None)
 ev[1].record(); torch.cuda.synchronize()
-print("lib", os.environ.get("G2LIB", "default"), "H", H, "us per launch (back-to-back, warm L2): %.1f" % (ev[0].elapsed_time(ev[1]) * 100))
+print("gconv", VER, "Cin", Cin, "Cout", Cout, "H", H, "us per launch (back-to-back, warm L2): %.1f" % (ev[0].elapsed_time(ev[1]) * 100))
 buf = (C.c_longlong * (148 * 64))()
-lib.hdmoe_g2_trace_read.argtypes = [C.c_void_p]
-lib.hdmoe_g2_trace_read(buf)
+rd = getattr(lib, 'hdmoe_g%s_trace_read' % VER)
+rd.argtypes = [C.c_void_p]
+rd(buf)
 a = np.array(buf[:], dtype=np.int64).reshape(148, 8, 8)
 for b in (0, 147):
     print("CTA", b)
