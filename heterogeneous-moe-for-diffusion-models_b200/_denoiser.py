@@ -96,6 +96,15 @@ class _fork:
                 t.record_stream(main)
 
 
+# channels-last tail of HDMOEM.forward with the fused swap / gate kernels (csrc/trunk_glue.cu); off = the reference's
+# op-by-op chain (kept for A/B parity tests)
+_FUSED_GLUE = [True]
+
+
+def set_fused_glue(enabled: bool) -> None:
+    _FUSED_GLUE[0] = bool(enabled)
+
+
 # expert parallelism for the U-Net MoE layer; None = every rank runs all experts (pure DP)
 _EP = {"placement": None, "group": None}
 
@@ -113,8 +122,20 @@ def disable_expert_parallel() -> None:
     _EP["placement"] = _EP["group"] = None
 
 
-def _run_experts_on_rows(experts, plan, xr, tr, txr):
-    """experts on expert-major rows: grouped tcgen05 path when possible, per-expert loop otherwise."""
+def _run_experts_on_rows(experts, plan, xr, tr, txr, nhwc_out: bool = False):
+    """experts on expert-major rows: grouped tcgen05 path when possible, per-expert loop otherwise.  nhwc_out: rows come
+    back channels-last [cap, H, W, C] (natively from the grouped / fused runners, converted otherwise)."""
+    if nhwc_out:
+        native = None
+        if (xr.dtype == torch.bfloat16 and _GROUPED[0] and len(experts) > 0
+                and all(isinstance(ex, mc.Unet_expert) for ex in experts) and _groupable(experts, xr)):
+            native = "unet"
+        elif _SYNC_FREE[0] and all(isinstance(ex, mc.Vit_expert) for ex in experts):
+            from . import vit_fused
+            if vit_fused.fusable(experts, xr):
+                native = "vit"
+        if native is None:
+            return _run_experts_on_rows(experts, plan, xr, tr, txr).permute(0, 2, 3, 1).contiguous()
     if (xr.dtype == torch.bfloat16 and _GROUPED[0] and len(experts) > 0
             and all(isinstance(ex, mc.Unet_expert) for ex in experts) and _groupable(experts, xr)):
         from .grouped import GroupedUnetExperts
@@ -124,7 +145,7 @@ def _run_experts_on_rows(experts, plan, xr, tr, txr):
         if runner is None:
             runner = GroupedUnetExperts(experts)
             holder[key] = runner
-        return runner(plan, xr, tr, txr, training=experts[0].training).contiguous()
+        return runner(plan, xr, tr, txr, training=experts[0].training, nhwc_out=nhwc_out).contiguous()
     if _SYNC_FREE[0] and all(isinstance(ex, mc.Vit_expert) for ex in experts):
         from . import vit_fused
         if vit_fused.fusable(experts, xr):
@@ -134,7 +155,7 @@ def _run_experts_on_rows(experts, plan, xr, tr, txr):
             if runner is None:
                 runner = vit_fused.FusedVitExperts(experts)
                 holder["_hdmoe_fused_vit"] = runner
-            return runner(plan, xr, tr, txr)
+            return runner(plan, xr, tr, txr, nhwc_out=nhwc_out)
         # Sync-free (CUDA-graph-capturable) execution of the cheap ViT experts (5-13 MFLOP per sample):
         # every expert sees all rows with static shapes and its rows are selected on the device; the reference's
         # "only experts that received samples run" rule for the train-mode weight rewrite is kept by a device flag.
@@ -181,8 +202,9 @@ def _run_experts_on_rows(experts, plan, xr, tr, txr):
 
 def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: torch.Tensor,
                            time_emb: torch.Tensor, text_emb: Optional[torch.Tensor],
-                           top_k: Optional[int] = None) -> torch.Tensor:
+                           top_k: Optional[int] = None, nhwc_out: bool = False) -> torch.Tensor:
     """One MoE layer: same signature and result as the reference helper (models/model_config2.py:11-39).
+    `nhwc_out` (B200 extra, used by HDMOEM's channels-last tail): the result comes back as [B, H, W, C].
 
     dispatch plan (bit-exact, expert-major / token-ascending, criterion weight > 0) -> ONE fused gather of
     the image rows, time rows and mean-pooled text rows -> experts on contiguous row ranges -> ONE
@@ -198,14 +220,15 @@ def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: 
         def run_local(local_ids, lplan, xr_, tr_, txr_):
             return _run_experts_on_rows([experts[i] for i in local_ids], lplan, xr_, tr_, txr_)
 
-        return EP.ep_moe_layer(x, out_router, time_emb, text_emb, run_local, _EP["placement"], k, group=_EP["group"],
-                               payload_dtype=dt)
+        out = EP.ep_moe_layer(x, out_router, time_emb, text_emb, run_local, _EP["placement"], k, group=_EP["group"],
+                              payload_dtype=dt)
+        return out.permute(0, 2, 3, 1).contiguous() if nhwc_out else out
     plan = ops.dispatch_plan(out_router, top_k)
     srcs = [x.to(dt), time_emb.to(dt)] + ([text_emb.to(dt)] if text_emb is not None else [])
     rows = ops.permute(plan, *srcs)
     xr, tr = rows[0], rows[1]
     txr = rows[2] if text_emb is not None else None
-    out_rows = _run_experts_on_rows(experts, plan, xr, tr, txr)
+    out_rows = _run_experts_on_rows(experts, plan, xr, tr, txr, nhwc_out=nhwc_out)
     return ops.combine(out_rows, out_router, plan, base=None, out_dtype=x.dtype)
 
 
@@ -321,6 +344,7 @@ class HDMOEM(nn.Module):
         pool_vit = pool_un = None
         if trunk is not None:
             pool_vit, pool_un = trunk([in_vit, in_unet], self.training)
+        glue = _FUSED_GLUE[0] and x.is_cuda and x.dtype == torch.float32 and self.internal_channels == 32
         # the ViT router is evaluated first (RNG order, quirk Q2)
         if _BRANCH_STREAMS[0] and x.is_cuda and _EP["placement"] is None:
             # ViT branch (router + MoE layer) beside the U-Net branch; host program order as in the reference
@@ -329,17 +353,34 @@ class HDMOEM(nn.Module):
                                                         noise=noise.get("vit"), pooled=pool_vit)
             w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
                                                   noise=noise.get("unet"), pooled=pool_un)
-            out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k)
+            out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k, nhwc_out=glue)
             with torch.cuda.stream(fk.s):
-                out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k)
+                out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k,
+                                               nhwc_out=glue)
             fk.join(w_vit, p_vit, raw_vit, out_v)
         else:
             w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
                                                     noise=noise.get("vit"), pooled=pool_vit)
             w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
                                                   noise=noise.get("unet"), pooled=pool_un)
-            out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k)
-            out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k)
+            out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k, nhwc_out=glue)
+            out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k, nhwc_out=glue)
+        if glue:
+            # channels-last tail: out_u / out_v are [B, H, W, C]; swap (cfg1) and the whole text-blend / gate / mix chain
+            # are one fused kernel each (csrc/trunk_glue.cu); output_proj reads the mix through a channels-last view
+            C = self.internal_channels
+            uf, vf = out_u.reshape(B, H * W, C), out_v.reshape(B, H * W, C)
+            if self._variant == 2:
+                q, ctx = uf, vf
+            else:
+                stronger = torch.sigmoid(alpha_routing * (s_vit - s_unet)).reshape(-1)
+                q, ctx = ops.trunk_swap(uf, vf, stronger)
+            a = self.cross_attn(query=q, context=ctx, gain_s=1.0, gain_t=1.0)
+            b = self.cross_attn_text(query=a, context=text_emb, gain_s=1.0, gain_t=1.0)
+            mix, g = ops.trunk_gate(uf, a, b, self.alpha_txt, self.gate1.prepared_weight(1.0, torch.float32),
+                                    self.gate2.prepared_weight(1.0, torch.float32), H, W)
+            out = self.output_proj(mix.reshape(B, H, W, C).permute(0, 3, 1, 2))
+            return out, p_un, raw_un, p_vit, raw_vit, scaling, g
         uf = out_u.flatten(2).transpose(1, 2)
         vf = out_v.flatten(2).transpose(1, 2)
         if self._variant == 2:

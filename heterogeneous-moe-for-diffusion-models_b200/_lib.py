@@ -28,6 +28,11 @@ class WprepBwdDesc(C.Structure):
                 ("cin_pad", C.c_int32), ("layout", C.c_int32), ("block_start", C.c_int32)]
 
 
+class OptTensorDesc(C.Structure):
+    _fields_ = [("p", _p), ("g", _p), ("m", _p), ("v", _p), ("numel", C.c_int64), ("lr", _f), ("weight_decay", _f),
+                ("chunk_start", C.c_int32), ("pad", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/hdmoe_b200.h one to one
 PROTOTYPES = {
     "hdmoe_version": (_i, []),
@@ -75,6 +80,13 @@ PROTOTYPES = {
     "hdmoe_wprep_bwd_multi_resident": (_i, [_p, _i, _i, _p]),
     "hdmoe_wprep_bwd_multi": (_i, [_p, _p, _i, _p]),
     "hdmoe_wprep_bwd": (_i, [_p, _p, _p, _f, _i, _i, _p, _p, _p]),
+    "hdmoe_trunk_swap_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i64, _p]),
+    "hdmoe_trunk_swap_slices": (_i, []),
+    "hdmoe_trunk_swap_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _p]),
+    "hdmoe_trunk_gate_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _f, _f, _p]),
+    "hdmoe_trunk_gate_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _f, _f, _p]),
+    "hdmoe_optim_chunk_elems": (_i, []),
+    "hdmoe_adamw_step": (_i, [_p, _i, _i, _p, _p, _p, _f, _f, _f, _f, _i, _p]),
 }
 
 _lib = None

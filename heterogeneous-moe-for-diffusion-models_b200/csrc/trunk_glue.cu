@@ -1,0 +1,376 @@
+// HDMOEM.forward glue between the two MoE layers and output_proj (models/model_config2.py:276-302, the cfg1 soft
+// query / context swap of models/model_config1.py:277-283) as fused per-pixel kernels on channels-last fp32 activations
+// [P = B*H*W, C]: the reference runs ~25 elementwise / 1x1-convolution launches forward and ~50 backward over
+// activation-sized tensors here (25 % of the device time of the round-1 train step).
+//
+//   swap   q = w*v + (1-w)*u,  ctx = w*u + (1-w)*v           w[b] = sigmoid(alpha_routing * (s_vit - s_unet))   (cfg1)
+//   gate   fin  = a + alpha_txt * (b - a)                                                       (:291)
+//          xcat = mp_cat(u, fin)  ->  h = W1 xcat  ->  mp_silu  ->  l = W2 (.)  ->  g = softmax_2(l)          (:293-297)
+//          mix  = mp_sum(u, g0*u + g1*fin, 0.5)                                                 (:298-301)
+//
+// One thread owns one pixel's channel vector (C = 32: 128 contiguous bytes); W1 / W2 are broadcast from shared
+// memory.  The backward kernel recomputes the forward per pixel, writes du / da / db, and accumulates the gate weight
+// gradients in registers across all pixels a persistent CTA visits (per-thread 2 x 4 tile of dW1 fed from a shared-
+// memory staging of the CTA's pixel batch), so they cost one vector atomic set per CTA.  HBM-bound: forward 520 B,
+// backward 900 B per pixel.
+#include "common.cuh"
+
+namespace hdmoe {
+
+constexpr int kGC = 32;            // internal channels (Utils/configs.py:8)
+constexpr int kGT = 256;           // threads per CTA = pixels per batch
+
+__device__ __forceinline__ float silu_mp(float x) { return x / (1.f + __expf(-x)) * (1.f / 0.596f); }
+__device__ __forceinline__ float dsilu_mp(float x) {
+    const float s = 1.f / (1.f + __expf(-x));
+    return s * (1.f + x * (1.f - s)) * (1.f / 0.596f);
+}
+
+// ------------------------------------------------------------------------------------------------ swap
+__global__ void __launch_bounds__(256)
+swap_fwd_kernel(const float4* __restrict__ u, const float4* __restrict__ v, const float* __restrict__ w, float4* __restrict__ q,
+                float4* __restrict__ ctx, long long n4, long long per_sample4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float wb = w[i / per_sample4], wc = 1.f - wb;
+        const float4 a = u[i], b = v[i];
+        q[i] = make_float4(wb * b.x + wc * a.x, wb * b.y + wc * a.y, wb * b.z + wc * a.z, wb * b.w + wc * a.w);
+        ctx[i] = make_float4(wb * a.x + wc * b.x, wb * a.y + wc * b.y, wb * a.z + wc * b.z, wb * a.w + wc * b.w);
+    }
+}
+
+// one CTA per (sample, slice): du, dv and the partial of dw[b] = sum (v - u) * (dq - dctx)
+__global__ void __launch_bounds__(256)
+swap_bwd_kernel(const float4* __restrict__ u, const float4* __restrict__ v, const float* __restrict__ w,
+                const float4* __restrict__ dq, const float4* __restrict__ dctx, float4* __restrict__ du, float4* __restrict__ dv,
+                float* __restrict__ dw_part, long long per_sample4, int slices) {
+    __shared__ float red[8];
+    const int b = blockIdx.x / slices, sl = blockIdx.x - b * slices;
+    const float wb = w[b], wc = 1.f - wb;
+    const long long lo = (long long)b * per_sample4 + per_sample4 * sl / slices;
+    const long long hi = (long long)b * per_sample4 + per_sample4 * (sl + 1) / slices;
+    float acc = 0.f;
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+        const float4 a = u[i], c = v[i], gq = dq[i], gc = dctx[i];
+        du[i] = make_float4(wc * gq.x + wb * gc.x, wc * gq.y + wb * gc.y, wc * gq.z + wb * gc.z, wc * gq.w + wb * gc.w);
+        dv[i] = make_float4(wb * gq.x + wc * gc.x, wb * gq.y + wc * gc.y, wb * gq.z + wc * gc.z, wb * gq.w + wc * gc.w);
+        acc += (c.x - a.x) * (gq.x - gc.x) + (c.y - a.y) * (gq.y - gc.y) + (c.z - a.z) * (gq.z - gc.z) +
+               (c.w - a.w) * (gq.w - gc.w);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        dw_part[blockIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ gate
+struct GateConsts {
+    float c1, c2;          // mp_cat weights of u and fin
+    float ms_a, ms_b;      // mp_sum(u, gated, t): (1-t)/norm, t/norm
+};
+
+__device__ __forceinline__ void load_vec32(const float* __restrict__ p, float (&x)[kGC]) {
+#pragma unroll
+    for (int i = 0; i < kGC / 4; ++i) {
+        const float4 t = reinterpret_cast<const float4*>(p)[i];
+        x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void store_vec32(float* __restrict__ p, const float (&x)[kGC]) {
+#pragma unroll
+    for (int i = 0; i < kGC / 4; ++i)
+        reinterpret_cast<float4*>(p)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+}
+
+// W1 in shared memory as [i][j] (input-major) so that a thread's loop over j for fixed i reads consecutive words that
+// every thread of the warp reads identically (broadcast)
+__global__ void __launch_bounds__(kGT)
+gate_fwd_kernel(const float* __restrict__ u, const float* __restrict__ a, const float* __restrict__ b,
+                const float* __restrict__ alpha_p, const float* __restrict__ W1, const float* __restrict__ W2,
+                float* __restrict__ mix, float* __restrict__ g_out, long long P, long long HW, GateConsts k) {
+    extern __shared__ float sm[];
+    float* w1s = sm;                               // [i (64)][j (32)]
+    float* w2s = w1s + 2 * kGC * kGC;              // [2][32]
+    float* s_xc = w2s + 2 * kGC;                   // [kGT][65]: this thread's xcat column (runtime-indexed in the matvec)
+    for (int t = threadIdx.x; t < 2 * kGC * kGC; t += kGT) {
+        const int j = t / (2 * kGC), i = t - j * 2 * kGC;      // W1 is [j][i] row-major
+        w1s[i * kGC + j] = W1[t];
+    }
+    if (threadIdx.x < 2 * kGC) w2s[threadIdx.x] = W2[threadIdx.x];
+    __syncthreads();
+    const float alpha = *alpha_p;
+    float* my_xc = s_xc + threadIdx.x * (2 * kGC + 1);
+    for (long long p = (long long)blockIdx.x * kGT + threadIdx.x; p < P; p += (long long)gridDim.x * kGT) {
+        float x[kGC], f[kGC], h[kGC];
+        load_vec32(u + p * kGC, x);
+        {
+            float ta[kGC];
+            load_vec32(a + p * kGC, ta);
+            load_vec32(b + p * kGC, f);
+#pragma unroll
+            for (int c = 0; c < kGC; ++c) f[c] = ta[c] + alpha * (f[c] - ta[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < kGC; ++c) {
+            my_xc[c] = k.c1 * x[c];
+            my_xc[kGC + c] = k.c2 * f[c];
+        }
+#pragma unroll
+        for (int j = 0; j < kGC; ++j) h[j] = 0.f;
+#pragma unroll 2
+        for (int i = 0; i < 2 * kGC; ++i) {
+            const float xi = my_xc[i];
+            const float4* wr = reinterpret_cast<const float4*>(w1s + i * kGC);
+#pragma unroll
+            for (int j4 = 0; j4 < kGC / 4; ++j4) {
+                const float4 w = wr[j4];
+                h[4 * j4] = fmaf(w.x, xi, h[4 * j4]);
+                h[4 * j4 + 1] = fmaf(w.y, xi, h[4 * j4 + 1]);
+                h[4 * j4 + 2] = fmaf(w.z, xi, h[4 * j4 + 2]);
+                h[4 * j4 + 3] = fmaf(w.w, xi, h[4 * j4 + 3]);
+            }
+        }
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kGC; ++j) {
+            const float s = silu_mp(h[j]);
+            l0 = fmaf(w2s[j], s, l0);
+            l1 = fmaf(w2s[kGC + j], s, l1);
+        }
+        const float m = fmaxf(l0, l1), e0 = __expf(l0 - m), e1 = __expf(l1 - m), inv = 1.f / (e0 + e1);
+        const float g0 = e0 * inv, g1 = e1 * inv;
+#pragma unroll
+        for (int c = 0; c < kGC; ++c) x[c] = k.ms_a * x[c] + k.ms_b * (g0 * x[c] + g1 * f[c]);
+        store_vec32(mix + p * kGC, x);
+        // out_gate in the reference's [B, 2, H, W] layout
+        const long long bi = p / HW, px = p - bi * HW;
+        g_out[(bi * 2) * HW + px] = g0;
+        g_out[(bi * 2 + 1) * HW + px] = g1;
+    }
+}
+
+// Backward.  dW1 [32][64] and dW2 [2][32] are accumulated per CTA: every batch of kGT pixels is staged in shared memory
+// (d_h [kGT][32], xcat [kGT][64], dl [kGT][2], hs [kGT][32]) and thread t adds its 2 x 4 tile of dW1 (j in {2*(t/16),
+// +1}, i in {4*(t%16) .. +3}) over the batch; dW2 is owned by threads 0..63.  d_alpha is reduced per CTA.
+__global__ void __launch_bounds__(kGT)
+gate_bwd_kernel(const float* __restrict__ u, const float* __restrict__ a, const float* __restrict__ b,
+                const float* __restrict__ alpha_p, const float* __restrict__ W1, const float* __restrict__ W2,
+                const float* __restrict__ d_mix, const float* __restrict__ d_g, float* __restrict__ du, float* __restrict__ da,
+                float* __restrict__ db, float* __restrict__ dW1, float* __restrict__ dW2, float* __restrict__ d_alpha,
+                long long P, long long HW, GateConsts k) {
+    extern __shared__ float sm[];
+    float* w1s = sm;                               // [64][32]  (input-major, as forward)
+    float* w1t = w1s + 2 * kGC * kGC;              // [32][64]  (output-major: d_xcat = W1^T d_h)
+    float* w2s = w1t + 2 * kGC * kGC;              // [2][32]
+    float* s_dh = w2s + 2 * kGC;                   // [kGT][33]  (padded rows: column reads without bank conflicts)
+    float* s_xc = s_dh + kGT * (kGC + 1);          // [kGT][65]
+    float* s_dl = s_xc + kGT * (2 * kGC + 1);      // [kGT][2]
+    float* s_hs = s_dl + kGT * 2;                  // [kGT][33]
+    __shared__ float red[8];
+    for (int t = threadIdx.x; t < 2 * kGC * kGC; t += kGT) {
+        const int j = t / (2 * kGC), i = t - j * 2 * kGC;
+        w1s[i * kGC + j] = W1[t];
+        w1t[t] = W1[t];
+    }
+    if (threadIdx.x < 2 * kGC) w2s[threadIdx.x] = W2[threadIdx.x];
+    __syncthreads();
+    const float alpha = *alpha_p;
+    const int tj = 2 * (threadIdx.x >> 4), ti = 4 * (threadIdx.x & 15);
+    float acc1[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float acc2 = 0.f, acc_alpha = 0.f;
+    const long long nbatch = (P + kGT - 1) / kGT;
+    for (long long bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+        const long long p = bt * kGT + threadIdx.x;
+        const bool live = p < P;
+        float dh[kGC];
+        float dl0 = 0.f, dl1 = 0.f;
+        if (live) {
+            float x[kGC], f[kGC], h[kGC], diff[kGC];          // diff = b - a (d_alpha needs it; a, b themselves do not stay live)
+            load_vec32(u + p * kGC, x);
+            load_vec32(a + p * kGC, f);
+            load_vec32(b + p * kGC, diff);
+#pragma unroll
+            for (int c = 0; c < kGC; ++c) {
+                diff[c] -= f[c];
+                f[c] = fmaf(alpha, diff[c], f[c]);
+            }
+            float* my_xc = s_xc + threadIdx.x * (2 * kGC + 1);
+#pragma unroll
+            for (int c = 0; c < kGC; ++c) {
+                my_xc[c] = k.c1 * x[c];
+                my_xc[kGC + c] = k.c2 * f[c];
+            }
+#pragma unroll
+            for (int j = 0; j < kGC; ++j) h[j] = 0.f;
+#pragma unroll 2
+            for (int i = 0; i < 2 * kGC; ++i) {
+                const float xi = my_xc[i];
+                const float4* wr = reinterpret_cast<const float4*>(w1s + i * kGC);
+#pragma unroll
+                for (int j4 = 0; j4 < kGC / 4; ++j4) {
+                    const float4 w = wr[j4];
+                    h[4 * j4] = fmaf(w.x, xi, h[4 * j4]);
+                    h[4 * j4 + 1] = fmaf(w.y, xi, h[4 * j4 + 1]);
+                    h[4 * j4 + 2] = fmaf(w.z, xi, h[4 * j4 + 2]);
+                    h[4 * j4 + 3] = fmaf(w.w, xi, h[4 * j4 + 3]);
+                }
+            }
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < kGC; ++j) {
+                const float s = silu_mp(h[j]);
+                s_hs[threadIdx.x * (kGC + 1) + j] = s;
+                l0 = fmaf(w2s[j], s, l0);
+                l1 = fmaf(w2s[kGC + j], s, l1);
+            }
+            const float m = fmaxf(l0, l1), e0 = __expf(l0 - m), e1 = __expf(l1 - m), inv = 1.f / (e0 + e1);
+            const float g0 = e0 * inv, g1 = e1 * inv;
+            // mix = ms_a * u + ms_b * (g0 * u + g1 * f)
+            float gm[kGC];
+            load_vec32(d_mix + p * kGC, gm);
+            float dg0 = 0.f, dg1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < kGC; ++c) {
+                const float dgt = k.ms_b * gm[c];          // d gated
+                dg0 = fmaf(dgt, x[c], dg0);
+                dg1 = fmaf(dgt, f[c], dg1);
+            }
+            if (d_g) {
+                const long long bi = p / HW, px = p - bi * HW;
+                dg0 += d_g[(bi * 2) * HW + px];
+                dg1 += d_g[(bi * 2 + 1) * HW + px];
+            }
+            const float dot = g0 * dg0 + g1 * dg1;
+            dl0 = g0 * (dg0 - dot);
+            dl1 = g1 * (dg1 - dot);
+#pragma unroll
+            for (int j = 0; j < kGC; ++j) dh[j] = (w2s[j] * dl0 + w2s[kGC + j] * dl1) * dsilu_mp(h[j]);
+            // d xcat = W1^T d_h ; du = ms_a*gm + ms_b*g0*gm + c1*dxc_u ; dfin = ms_b*g1*gm + c2*dxc_f
+            float dfin[kGC];
+#pragma unroll
+            for (int i = 0; i < kGC; ++i) {
+                float su = 0.f, sf = 0.f;
+#pragma unroll
+                for (int j = 0; j < kGC; ++j) {
+                    su = fmaf(w1t[j * 2 * kGC + i], dh[j], su);
+                    sf = fmaf(w1t[j * 2 * kGC + kGC + i], dh[j], sf);
+                }
+                x[i] = (k.ms_a + k.ms_b * g0) * gm[i] + k.c1 * su;          // x now holds du
+                dfin[i] = k.ms_b * g1 * gm[i] + k.c2 * sf;
+                acc_alpha = fmaf(dfin[i], diff[i], acc_alpha);
+            }
+            store_vec32(du + p * kGC, x);
+#pragma unroll
+            for (int c = 0; c < kGC; ++c) diff[c] = (1.f - alpha) * dfin[c];
+            store_vec32(da + p * kGC, diff);
+#pragma unroll
+            for (int c = 0; c < kGC; ++c) dfin[c] *= alpha;
+            store_vec32(db + p * kGC, dfin);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kGC; ++j) dh[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2 * kGC; ++i) s_xc[threadIdx.x * (2 * kGC + 1) + i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < kGC; ++j) s_hs[threadIdx.x * (kGC + 1) + j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kGC; ++j) s_dh[threadIdx.x * (kGC + 1) + j] = dh[j];
+        s_dl[threadIdx.x * 2] = dl0;
+        s_dl[threadIdx.x * 2 + 1] = dl1;
+        __syncthreads();
+        // weight-gradient tiles over the batch
+#pragma unroll 4
+        for (int q = 0; q < kGT; ++q) {
+            const float d0 = s_dh[q * (kGC + 1) + tj], d1 = s_dh[q * (kGC + 1) + tj + 1];
+            const float* xr = s_xc + q * (2 * kGC + 1) + ti;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc1[0][c] = fmaf(d0, xr[c], acc1[0][c]);
+                acc1[1][c] = fmaf(d1, xr[c], acc1[1][c]);
+            }
+        }
+        if (threadIdx.x < 2 * kGC) {
+            const int kk = threadIdx.x >> 5, j = threadIdx.x & 31;
+            for (int q = 0; q < kGT; ++q) acc2 = fmaf(s_dl[q * 2 + kk], s_hs[q * (kGC + 1) + j], acc2);
+        }
+        __syncthreads();
+    }
+    // flush the CTA's partials
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) atomicAdd(dW1 + (tj + r) * 2 * kGC + ti + c, acc1[r][c]);
+    if (threadIdx.x < 2 * kGC) atomicAdd(dW2 + threadIdx.x, acc2);
+    acc_alpha = warp_sum(acc_alpha);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc_alpha;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < kGT / 32; ++i) t += red[i];
+        atomicAdd(d_alpha, t);
+    }
+}
+
+static constexpr int kGateFwdSmem = (2 * kGC * kGC + 2 * kGC + kGT * (2 * kGC + 1)) * (int)sizeof(float);
+static constexpr int kGateBwdSmem =
+    (2 * (2 * kGC * kGC) + 2 * kGC + kGT * (kGC + 1) + kGT * (2 * kGC + 1) + kGT * 2 + kGT * (kGC + 1)) * (int)sizeof(float);
+
+}  // namespace hdmoe
+using namespace hdmoe;
+
+extern "C" int hdmoe_trunk_swap_fwd(const float* u, const float* v, const float* w, float* q, float* ctx, int B,
+                                    int64_t per_sample, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(u && v && w && q && ctx && B >= 1 && per_sample >= 4 && per_sample % 4 == 0, "trunk_swap_fwd: bad args");
+    const long long n4 = (long long)B * per_sample / 4;
+    swap_fwd_kernel<<<grid_for(n4, 256, 16), 256, 0, (cudaStream_t)stream>>>((const float4*)u, (const float4*)v, w, (float4*)q,
+                                                                             (float4*)ctx, n4, per_sample / 4);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_trunk_swap_slices(void) { return 8; }
+
+extern "C" int hdmoe_trunk_swap_bwd(const float* u, const float* v, const float* w, const float* dq, const float* dctx,
+                                    float* du, float* dv, float* dw_part, int B, int64_t per_sample, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(u && v && w && dq && dctx && du && dv && dw_part && B >= 1 && per_sample >= 4 && per_sample % 4 == 0,
+                    "trunk_swap_bwd: bad args");
+    const int slices = hdmoe_trunk_swap_slices();
+    swap_bwd_kernel<<<B * slices, 256, 0, (cudaStream_t)stream>>>((const float4*)u, (const float4*)v, w, (const float4*)dq,
+                                                                  (const float4*)dctx, (float4*)du, (float4*)dv, dw_part,
+                                                                  per_sample / 4, slices);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_trunk_gate_fwd(const float* u, const float* a, const float* b, const float* alpha_txt, const float* W1,
+                                    const float* W2, float* mix, float* g_out, int64_t P, int64_t HW, int C, float c1,
+                                    float c2, float ms_a, float ms_b, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(u && a && b && alpha_txt && W1 && W2 && mix && g_out && P >= 1 && HW >= 1 && P % HW == 0, "trunk_gate_fwd: bad args");
+    HDMOE_CHECK_ARG(C == kGC, "trunk_gate_fwd: internal_channels must be %d (got %d)", kGC, C);
+    GateConsts k{c1, c2, ms_a, ms_b};
+    HDMOE_CHECK_CUDA(cudaFuncSetAttribute(gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateFwdSmem));
+    gate_fwd_kernel<<<grid_for(P, kGT, 3), kGT, kGateFwdSmem, (cudaStream_t)stream>>>(u, a, b, alpha_txt, W1, W2, mix, g_out, P, HW, k);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_trunk_gate_bwd(const float* u, const float* a, const float* b, const float* alpha_txt, const float* W1,
+                                    const float* W2, const float* d_mix, const float* d_g, float* du, float* da, float* db,
+                                    float* dW1, float* dW2, float* d_alpha, int64_t P, int64_t HW, int C, float c1, float c2,
+                                    float ms_a, float ms_b, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(u && a && b && alpha_txt && W1 && W2 && d_mix && du && da && db && dW1 && dW2 && d_alpha && P >= 1 &&
+                        HW >= 1 && P % HW == 0, "trunk_gate_bwd: bad args");
+    HDMOE_CHECK_ARG(C == kGC, "trunk_gate_bwd: internal_channels must be %d (got %d)", kGC, C);
+    GateConsts k{c1, c2, ms_a, ms_b};
+    HDMOE_CHECK_CUDA(cudaFuncSetAttribute(gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateBwdSmem));
+    const long long nbatch = (P + kGT - 1) / kGT;
+    const int grid = (int)(nbatch < kNumSMs ? nbatch : kNumSMs);      // persistent: dW partials stay in registers
+    gate_bwd_kernel<<<grid, kGT, kGateBwdSmem, (cudaStream_t)stream>>>(u, a, b, alpha_txt, W1, W2, d_mix, d_g, du, da, db, dW1, dW2,
+                                                                      d_alpha, P, HW, k);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}

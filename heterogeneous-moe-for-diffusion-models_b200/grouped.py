@@ -364,8 +364,9 @@ class GroupedUnetExperts:
     def _select(self, out_all, idx):
         return out_all[torch.arange(out_all.shape[0], device=out_all.device), idx]
 
-    def __call__(self, plan, x_rows, time_rows, text_rows, training: bool):
-        """x_rows [cap, C, H, W] (dispatch payload, any float dtype) -> [cap, C, H, W] bf16."""
+    def __call__(self, plan, x_rows, time_rows, text_rows, training: bool, nhwc_out: bool = False):
+        """x_rows [cap, C, H, W] (dispatch payload, any float dtype) -> [cap, C, H, W] bf16 ([cap, H, W, C] when
+        nhwc_out: the channels-last trunk consumes the expert output without a layout change)."""
         dev = x_rows.device
         if self._built_for != dev:
             self._build(dev)
@@ -434,4 +435,4 @@ class GroupedUnetExperts:
             if "encoders" in s["name"]:
                 skips.append(x)
         x = self._conv(x, self.out_li, token, use)
-        return nhwc.nhwc_to_rows(x)
+        return x if nhwc_out else nhwc.nhwc_to_rows(x)

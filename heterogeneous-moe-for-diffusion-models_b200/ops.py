@@ -746,3 +746,89 @@ def linear32(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
             and x.shape[-1] == 32 and x.numel() >= 32 * 4096 and torch.is_grad_enabled() and w.requires_grad):
         return _Linear32.apply(x, w)
     return torch.nn.functional.linear(x, w)
+
+
+# ----------------------------------------------------------------------------------------------------
+# (9) HDMOEM glue on channels-last activations (csrc/trunk_glue.cu)
+# ----------------------------------------------------------------------------------------------------
+class _TrunkSwap(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, v, w):
+        _cuda(u, v, w)
+        u, v, w = _f32c(u), _f32c(v), _f32c(w).reshape(-1)
+        B = u.shape[0]
+        per = u[0].numel()
+        assert v.shape == u.shape and w.numel() == B
+        q, c = torch.empty_like(u), torch.empty_like(u)
+        L.check(L.lib().hdmoe_trunk_swap_fwd(_p(u), _p(v), _p(w), _p(q), _p(c), B, per, _st()), "trunk_swap_fwd")
+        ctx.save_for_backward(u, v, w)
+        return q, c
+
+    @staticmethod
+    def backward(ctx, dq, dc):
+        u, v, w = ctx.saved_tensors
+        B, per = u.shape[0], u[0].numel()
+        dq = torch.zeros_like(u) if dq is None else _f32c(dq)
+        dc = torch.zeros_like(u) if dc is None else _f32c(dc)
+        du, dv = torch.empty_like(u), torch.empty_like(u)
+        sl = L.lib().hdmoe_trunk_swap_slices()
+        part = torch.empty(B, sl, dtype=torch.float32, device=u.device)
+        L.check(L.lib().hdmoe_trunk_swap_bwd(_p(u), _p(v), _p(w), _p(dq), _p(dc), _p(du), _p(dv), _p(part), B, per, _st()),
+                "trunk_swap_bwd")
+        return du, dv, part.sum(dim=1)
+
+
+def trunk_swap(u, v, w):
+    """cfg1 soft query / context swap (models/model_config1.py:277-283): (w*v + (1-w)*u, w*u + (1-w)*v) with one
+    weight per sample; u, v [B, ...] fp32 of any (equal) trailing shape."""
+    return _TrunkSwap.apply(u, v, w)
+
+
+class _TrunkGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, a, b, alpha, W1, W2, H, W, consts):
+        _cuda(u, a, b, alpha, W1, W2)
+        u, a, b = _f32c(u), _f32c(a), _f32c(b)
+        ctx.in_shapes = (tuple(alpha.shape), tuple(W1.shape), tuple(W2.shape))
+        W1, W2, alpha = _f32c(W1).reshape(W1.shape[0], -1), _f32c(W2).reshape(W2.shape[0], -1), _f32c(alpha).reshape(1)
+        Cn = u.shape[-1]
+        P = u.numel() // Cn
+        HW = H * W
+        if W1.shape != (Cn, 2 * Cn) or W2.shape != (2, Cn) or a.shape != u.shape or b.shape != u.shape:
+            raise RuntimeError("trunk_gate: shapes must be u, a, b [P, C], W1 [C, 2C], W2 [2, C]")
+        mix = torch.empty_like(u)
+        g = torch.empty(P // HW, 2, H, W, dtype=torch.float32, device=u.device)
+        L.check(L.lib().hdmoe_trunk_gate_fwd(_p(u), _p(a), _p(b), _p(alpha), _p(W1), _p(W2), _p(mix), _p(g), P, HW, Cn,
+                                             *consts, _st()), "trunk_gate_fwd")
+        ctx.save_for_backward(u, a, b, alpha, W1, W2)
+        ctx.meta = (P, HW, Cn, consts)
+        return mix, g
+
+    @staticmethod
+    def backward(ctx, d_mix, d_g):
+        u, a, b, alpha, W1, W2 = ctx.saved_tensors
+        P, HW, Cn, consts = ctx.meta
+        d_mix = torch.zeros_like(u) if d_mix is None else _f32c(d_mix)
+        d_g = None if d_g is None else _f32c(d_g)
+        du, da, db = torch.empty_like(u), torch.empty_like(u), torch.empty_like(u)
+        acc = torch.zeros(W1.numel() + W2.numel() + 1, dtype=torch.float32, device=u.device)
+        dW1, dW2, d_alpha = acc[:W1.numel()], acc[W1.numel():W1.numel() + W2.numel()], acc[-1:]
+        L.check(L.lib().hdmoe_trunk_gate_bwd(_p(u), _p(a), _p(b), _p(alpha), _p(W1), _p(W2), _p(d_mix), _p(d_g), _p(du), _p(da),
+                                             _p(db), _p(dW1), _p(dW2), _p(d_alpha), P, HW, Cn, *consts, _st()),
+                "trunk_gate_bwd")
+        sa, s1, s2 = ctx.in_shapes
+        return du, da, db, d_alpha.reshape(sa), dW1.reshape(s1), dW2.reshape(s2), None, None, None
+
+
+def trunk_gate(u, a, b, alpha_txt, w1_hat, w2_hat, H: int, W: int, cat_t: float = 0.5, sum_t: float = 0.5):
+    """Text blend + gated mix of HDMOEM.forward (models/model_config2.py:291-301) on channels-last activations.
+    u (U-Net MoE output), a (cross_attn output), b (cross_attn_text output): [B, H*W, C] fp32; alpha_txt 0-dim;
+    w1_hat / w2_hat: the PREPARED gate1 [C, 2C(,1,1)] / gate2 [2, C(,1,1)] weights.  Returns (mix [B, H*W, C] -- the input
+    of output_proj --, out_gate [B, 2, H, W])."""
+    import math
+    Cn = u.shape[-1]
+    c = math.sqrt((2 * Cn) / ((1 - cat_t) ** 2 + cat_t ** 2))
+    c1, c2 = c * (1 - cat_t) / math.sqrt(Cn), c * cat_t / math.sqrt(Cn)
+    n = math.sqrt((1 - sum_t) ** 2 + sum_t ** 2)
+    consts = (float(c1), float(c2), float((1 - sum_t) / n), float(sum_t / n))
+    return _TrunkGate.apply(u, a, b, alpha_txt, w1_hat, w2_hat, H, W, consts)

@@ -155,7 +155,7 @@ class FusedVitExperts:
                           ex.norm.weight, ex.norm.bias, blk.TMSA.rel_pos_bias.reshape(-1)]
         return torch.cat([p.float() for p in parts])
 
-    def __call__(self, plan, xr, tr, txr):
+    def __call__(self, plan, xr, tr, txr, nhwc_out: bool = False):
         experts, training = self.experts, self.experts[0].training
         R = xr.shape[0]
         x32, t32 = xr.float(), tr.float()
@@ -194,10 +194,17 @@ class FusedVitExperts:
                 p, hp, wp, ph, pw, H, W, sel = geo[e]
                 with m.active_flag(plan.counts[e] > 0):
                     y = ex.unpatch_proj(out[:, :ex.seq_ln].reshape(R * ex.seq_ln, _EMB))
-                y = y.reshape(R, ex.seq_ln, -1).transpose(1, 2).reshape(R, -1, hp, wp)
-                y = ex.unpatch(y)
-                if ph or pw:
-                    y = y[:, :, :H, :W]
+                if nhwc_out:
+                    # PixelShuffle straight into channels-last: out[r, h*p+i, w*p+j, c] = y[r, (h, w), c*p*p + i*p + j]
+                    Cn = y.shape[-1] // (p * p)
+                    y = y.reshape(R, hp, wp, Cn, p, p).permute(0, 1, 4, 2, 5, 3).reshape(R, hp * p, wp * p, Cn)
+                    if ph or pw:
+                        y = y[:, :H, :W, :]
+                else:
+                    y = y.reshape(R, ex.seq_ln, -1).transpose(1, 2).reshape(R, -1, hp, wp)
+                    y = ex.unpatch(y)
+                    if ph or pw:
+                        y = y[:, :, :H, :W]
                 y = torch.where(sel.view(-1, 1, 1, 1), y, torch.zeros((), dtype=y.dtype, device=y.device))
                 res = y if res is None else res + y
         return res.to(xr.dtype)

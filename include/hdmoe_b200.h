@@ -306,6 +306,47 @@ int hdmoe_nhwc_to_nchw(const void* src, void* dst, int64_t rows, int Cs, int Cd,
  *     experts of one layer in a single persistent launch.  Declared in hdmoe_gemm.h.
  * ---------------------------------------------------------------------------------------------- */
 
+/* ------------------------------------------------------------------------------------------------
+ * (10) Optimizer side of the train step -- replaces torch.nn.utils.clip_grad_norm_(parameters, max_norm) followed by
+ *      AdamW.step() (Utils/training.py:195-197) over all parameter tensors with three launches.
+ *      table_dev: device array of n_tensors descriptors
+ *          { float* p, g, m, v; int64 numel; float lr, weight_decay; int32 chunk_start, pad }   (56 bytes)
+ *      where tensor i owns chunks [chunk_start, chunk_start + ceil(numel / hdmoe_optim_chunk_elems())); g == NULL skips
+ *      the tensor (a parameter without a gradient, as torch does).  partial: n_chunks floats of scratch.
+ *      state[3] (device, fp32): [0] number of calls (incremented), [1] total gradient norm (output),
+ *      [2] clip coefficient min(1, max_norm / (norm + 1e-6)) (output; max_norm <= 0: no clipping).
+ *      steps[n_tensors] (device, fp32): per-tensor update count (torch.optim.AdamW semantics), incremented for every
+ *      tensor with a gradient and used for its bias correction.
+ *      write_back_grad != 0 stores the clipped gradients like clip_grad_norm_ does in place.
+ * ---------------------------------------------------------------------------------------------- */
+int hdmoe_optim_chunk_elems(void);
+int hdmoe_adamw_step(const void* table_dev, int n_tensors, int n_chunks, float* partial, float* state, float* steps,
+                     float max_norm, float beta1, float beta2, float eps, int write_back_grad, hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (11) HDMOEM.forward glue on channels-last fp32 activations [P = B*H*W, C = 32] -- replaces the elementwise / 1x1
+ *      convolution chains of models/model_config2.py:291-301 (text blend, mp_cat -> gate1 -> mp_silu -> gate2 -> pixel
+ *      softmax -> blend -> mp_sum) and the cfg1 soft query / context swap of models/model_config1.py:277-283.
+ *      swap:  q = w[b] * v + (1 - w[b]) * u,  ctx = w[b] * u + (1 - w[b]) * v     (per_sample = H*W*C elements per b)
+ *             bwd writes du, dv and dw_part [B * hdmoe_trunk_swap_slices()] (sum over the slices of b = d w[b]).
+ *      gate:  fin = a + *alpha_txt * (b - a);  h = W1 [c1*u ; c2*fin]  (W1 [32, 64] prepared gate1 weight);
+ *             g = softmax(W2 mp_silu(h))  (W2 [2, 32]);  mix = ms_a*u + ms_b*(g0*u + g1*fin);
+ *             g_out is [B, 2, H, W] (the reference's out_gate).  bwd: d_g may be NULL; dW1 / dW2 / d_alpha are
+ *             ACCUMULATED (zero them first).
+ * ---------------------------------------------------------------------------------------------- */
+int hdmoe_trunk_swap_fwd(const float* u, const float* v, const float* w, float* q, float* ctx, int B, int64_t per_sample,
+                         hdmoe_stream_t stream);
+int hdmoe_trunk_swap_slices(void);
+int hdmoe_trunk_swap_bwd(const float* u, const float* v, const float* w, const float* dq, const float* dctx, float* du,
+                         float* dv, float* dw_part, int B, int64_t per_sample, hdmoe_stream_t stream);
+int hdmoe_trunk_gate_fwd(const float* u, const float* a, const float* b, const float* alpha_txt, const float* W1,
+                         const float* W2, float* mix, float* g_out, int64_t P, int64_t HW, int C, float c1, float c2,
+                         float ms_a, float ms_b, hdmoe_stream_t stream);
+int hdmoe_trunk_gate_bwd(const float* u, const float* a, const float* b, const float* alpha_txt, const float* W1,
+                         const float* W2, const float* d_mix, const float* d_g, float* du, float* da, float* db,
+                         float* dW1, float* dW2, float* d_alpha, int64_t P, int64_t HW, int C, float c1, float c2,
+                         float ms_a, float ms_b, hdmoe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,68 @@
+"""Fused HDMOEM glue kernels (csrc/trunk_glue.cu) against the oracle's op-by-op arithmetic of models/model_config2.py:
+291-301 (text blend, mp_cat, gate1, mp_silu, gate2, pixel softmax, blend, mp_sum) and of the cfg1 soft swap
+(models/model_config1.py:277-283), forward and every gradient, in float64.  fp32 kernels: rel-L2 <= 1e-5."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+from oracle import hdmoe_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 8, 8), (5, 32, 32), (2, 20, 12)])
+def test_trunk_gate_matches_oracle_chain(B, H, W):
+    from hdmoe_b200 import ops
+    C = 32
+    gen = torch.Generator().manual_seed(B * H + W)
+    u, a, b = (torch.randn(B, H * W, C, generator=gen) for _ in range(3))
+    alpha = torch.tensor(0.37)
+    W1 = torch.randn(C, 2 * C, 1, 1, generator=gen) / (2 * C) ** 0.5
+    W2 = torch.randn(2, C, 1, 1, generator=gen) / C ** 0.5
+    gm = torch.randn(B, H * W, C, generator=gen)
+    gg = torch.randn(B, 2, H, W, generator=gen)
+    # oracle chain on NCHW tensors, float64
+    leaves = [t.double().requires_grad_(True) for t in (u, a, b, alpha, W1, W2)]
+    ur, ar, br, alr, w1r, w2r = leaves
+    nchw = lambda t: t.transpose(1, 2).reshape(B, C, H, W)
+    out_u = nchw(ur)
+    fin = ar + alr * (br - ar)
+    img = nchw(fin)
+    g = F.conv2d(O.mp_silu(F.conv2d(O.mp_cat(out_u, img, dim=1), w1r)), w2r)
+    g = F.softmax(g, dim=1)
+    gated = g[:, 0:1] * out_u + g[:, 1:2] * img
+    mix_ref = O.mp_sum(out_u, gated, t=0.5)
+    ((mix_ref.flatten(2).transpose(1, 2) * gm.double()).sum() + (g * gg.double()).sum()).backward()
+    dl = [t.cuda().requires_grad_(True) for t in (u, a, b, alpha, W1, W2)]
+    mix, gate = ops.trunk_gate(dl[0], dl[1], dl[2], dl[3], dl[4], dl[5], H, W)
+    ((mix * gm.cuda()).sum() + (gate * gg.cuda()).sum()).backward()
+    assert rel_l2(mix.cpu(), mix_ref.flatten(2).transpose(1, 2)) < 1e-5
+    assert rel_l2(gate.cpu(), g) < 1e-5
+    for got, ref, name in zip(dl, leaves, ("u", "a", "b", "alpha_txt", "gate1", "gate2")):
+        assert rel_l2(got.grad.cpu(), ref.grad) < 2e-5, name
+    # out_gate gradient absent (the usual case: out_gate is only logged)
+    dl2 = [t.detach().clone().requires_grad_(True) for t in dl]
+    mix2, _ = ops.trunk_gate(dl2[0], dl2[1], dl2[2], dl2[3], dl2[4], dl2[5], H, W)
+    (mix2 * gm.cuda()).sum().backward()
+    assert torch.isfinite(dl2[0].grad).all() and float(dl2[4].grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("B,S", [(4, 64), (7, 1024)])
+def test_trunk_swap_matches_oracle(B, S):
+    from hdmoe_b200 import ops
+    gen = torch.Generator().manual_seed(S)
+    u, v = torch.randn(B, S, 32, generator=gen), torch.randn(B, S, 32, generator=gen)
+    w = torch.rand(B, generator=gen)
+    gq, gc = torch.randn(B, S, 32, generator=gen), torch.randn(B, S, 32, generator=gen)
+    ur, vr, wr = (t.double().requires_grad_(True) for t in (u, v, w))
+    st = wr.view(-1, 1, 1)
+    q_ref = st * vr + (1 - st) * ur                 # models/model_config1.py:281-283
+    c_ref = st * ur + (1 - st) * vr
+    ((q_ref * gq.double()).sum() + (c_ref * gc.double()).sum()).backward()
+    ud, vd, wd = (t.cuda().requires_grad_(True) for t in (u, v, w))
+    q, c = ops.trunk_swap(ud, vd, wd)
+    ((q * gq.cuda()).sum() + (c * gc.cuda()).sum()).backward()
+    assert rel_l2(q.cpu(), q_ref) < 1e-6 and rel_l2(c.cpu(), c_ref) < 1e-6
+    assert rel_l2(ud.grad.cpu(), ur.grad) < 1e-6 and rel_l2(vd.grad.cpu(), vr.grad) < 1e-6
+    assert rel_l2(wd.grad.cpu(), wr.grad) < 1e-5
