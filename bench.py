@@ -157,75 +157,75 @@ class L2Flusher:
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import hdmoe_b200
-    from hdmoe_b200 import _lib
-    from hdmoe_b200.utils import EDM_LOSS
-    rank, world, local = dist_setup(args.gpus)
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    _lib.lib()     # fail loudly if the CUDA library is missing
-    torch.backends.cuda.matmul.allow_tf32 = True
-    torch.backends.cudnn.allow_tf32 = True
-    hdmoe_b200.set_expert_dtype(torch.bfloat16)
-    B = args.batch
-    if args.parallelism == "ep" and world > 1:
-        # U-Net experts sharded over the ranks (cost-balanced), NCCL all-to-all dispatch / combine; the split sizes
-        # are read on the host, so this mode runs the eager step (no whole-step graph)
-        hdmoe_b200.enable_expert_parallel([3, 3, 5, 5])
-        args.no_graph = True
-    model = build_model(1, device)
-    model.train()
-    crit = EDM_LOSS(**LOSS)
-    params = [p for p in model.parameters()]
-    from hdmoe_b200.optim import FusedAdamW
-    # clip_grad_norm_(1.0) + AdamW(lr 5e-4) of the reference loop, as the three-launch multi-tensor kernel set
-    opt = FusedAdamW(params, lr=5e-4, max_grad_norm=1.0)
-    flat_sizes = [p.numel() for p in params]
-    host = synth_batch(B, 32, rank, device, pinned=True)
-    dev_batch = {k: v.to(device) for k, v in host.items()}
-    zeta = 2.0
-    flush = L2Flusher(device)
+class TrainRunner:
+    """One training step of preconditioned_HDMOEM (variant 1 / 2) at `res` x `res`, batch B per GPU: forward
+    (return_log_var) + EDM_LOSS + backward + gradient all-reduce (world > 1) + gradient-norm clip 1.0 + AdamW, recorded
+    as CUDA graph(s) when possible.  parallelism: "dp" = replicas; "ep" = U-Net experts sharded over the ranks with the
+    static-shape all-to-all layer (expert_parallel.py), trunk data-parallel."""
 
-    def fwd_bwd(b):
-        out = model(x=b["x"], sigma=b["sigma"], text_emb=b["text"], Unet_router_mask=b["um"],
-                    Vit_router_mask=b["vm"], zeta=zeta, return_log_var=True)
-        loss = crit(b["sigma"], b["x0"], b["sigma"], out)
-        opt.zero_grad(set_to_none=True)
-        loss["loss"].backward()
-        return loss["loss"]
+    def __init__(self, variant, res, B, rank, world, device, parallelism="dp", use_graph=True, warmup=3, pinned=False):
+        import hdmoe_b200
+        from hdmoe_b200.optim import FusedAdamW
+        from hdmoe_b200.utils import EDM_LOSS
+        self.world, self.device, self.B = world, device, B
+        self.ep = parallelism == "ep" and world > 1
+        if self.ep:
+            hdmoe_b200.enable_expert_parallel([3, 3, 5, 5], capacity_factor=EP_CAPACITY)
+        else:
+            hdmoe_b200.disable_expert_parallel()
+        torch.manual_seed(0)
+        mod = hdmoe_b200.model_config1 if variant == 1 else hdmoe_b200.model_config2
+        model = mod.preconditioned_HDMOEM(**dict(FULL, IN_img_resolution=res))
+        gen = torch.Generator().manual_seed(100)
+        with torch.no_grad():
+            for p in model.parameters():
+                if float(p.abs().max()) == 0:
+                    p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
+        self.model = model.to(device).train()
+        crit = EDM_LOSS(**LOSS)
+        params = self.params = list(self.model.parameters())
+        # clip_grad_norm_(1.0) + AdamW(lr 5e-4) of the reference loop, as the three-launch multi-tensor kernel set
+        opt = self.opt = FusedAdamW(params, lr=5e-4, max_grad_norm=1.0)
+        flat_sizes = [p.numel() for p in params]
+        self.host = synth_batch(B, res, rank, device, pinned=pinned)
+        self.dev_batch = {k: v.to(device) for k, v in self.host.items()}
+        kw = dict(transition_point=P_MEAN, softness=P_STD) if variant == 2 else {}
 
-    def reduce_and_update():
-        if world > 1:
-            import torch.distributed as dist
-            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat)
-            flat.div_(world)
-            for p, g in zip(params, flat.split(flat_sizes)):
-                p.grad = g.view_as(p)
-        opt.step()                                   # gradient-norm clip (max 1.0) fused into the optimizer launches
+        def fwd_bwd(b):
+            out = self.model(x=b["x"], sigma=b["sigma"], text_emb=b["text"], Unet_router_mask=b["um"],
+                             Vit_router_mask=b["vm"], zeta=2.0, return_log_var=True, **kw)
+            loss = crit(b["sigma"], b["x0"], b["sigma"], out)["loss"]
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            return loss
 
-    def step(b):
-        loss = fwd_bwd(b)
-        reduce_and_update()
-        return loss
+        def step(b):
+            loss = fwd_bwd(b)
+            if world > 1:
+                import torch.distributed as dist
+                grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                dist.all_reduce(flat)
+                flat.div_(world)
+                for p, g in zip(params, flat.split(flat_sizes)):
+                    p.grad = g.view_as(p)
+            opt.step()                                # gradient-norm clip (max 1.0) fused into the optimizer launches
+            return loss
 
-    # whole-step CUDA graph.  The capture (and its own warm-up iterations) must be the FIRST thing that touches
-    # autograd: AccumulateGrad nodes created on the default stream by an earlier eager step would tie the legacy
-    # stream to the capturing stream.  If capture is impossible the process restarts itself in eager mode.
-    graphed, graph_note = None, "eager"
-    if not args.no_graph:
-        try:
+        self.eager_step = step
+        self.graphed, self.note = None, "eager"
+        if use_graph:
             from hdmoe_b200.train_step import GraphedTrainStep
+            # The capture (and its own warm-up iterations) must be the FIRST thing that touches autograd: AccumulateGrad
+            # nodes created on the default stream by an earlier eager step would tie the legacy stream to the capture.
             if world == 1:
-                graphed = GraphedTrainStep(step, dev_batch, warmup=max(3, args.warmup)).capture()
-                graph_note = "cuda_graph (whole step: fwd+loss+bwd+clip+AdamW)"
+                self.graphed = GraphedTrainStep(step, self.dev_batch, warmup=max(3, warmup)).capture()
+                self.note = "cuda_graph (whole step: fwd+loss+bwd+clip+AdamW)"
             else:
-                # N > 1: two graphs around ONE eager NCCL launch.  Graph A = forward + loss + backward + flatten of
-                # all gradients into a static buffer; the all-reduce of that buffer is the only eager launch; graph B
-                # = mean, clip_grad_norm_ and fused AdamW on views of the same buffer.  (The collective stays out of
-                # stream capture; the step costs 3 host launches instead of ~600.)
+                # N > 1: two graphs around ONE eager NCCL launch.  Graph A = forward + loss + backward (+ the expert-
+                # parallel all-to-alls in "ep" mode, captured) + flatten of all gradients into a static buffer; the
+                # all-reduce of that buffer is the only eager launch; graph B = mean, clip and AdamW on views of it.
+                import torch.distributed as dist
                 flat = torch.zeros(sum(flat_sizes), device=device)
 
                 def fwd_bwd_flat(b):
@@ -241,8 +241,7 @@ def run_ours(args):
                     opt.step()
                     return flat
 
-                import torch.distributed as dist
-                inner = GraphedTrainStep(fwd_bwd_flat, dev_batch, warmup=max(3, args.warmup)).capture()
+                inner = GraphedTrainStep(fwd_bwd_flat, self.dev_batch, warmup=max(3, warmup)).capture()
                 upd = GraphedTrainStep(update, {}, warmup=1).capture()
 
                 class _Outer:
@@ -255,19 +254,71 @@ def run_ours(args):
                         upd(None)
                         return loss
 
-                graphed = _Outer()
-                graph_note = "cuda_graph A (fwd+loss+bwd+flatten) + eager NCCL all-reduce + cuda_graph B (clip+AdamW)"
-        except Exception:                            # noqa: BLE001
-            import traceback
-            traceback.print_exc()
-            if world > 1:
-                raise
-            sys.stderr.write("bench.py: CUDA-graph capture failed, restarting in eager mode\n")
-            sys.stderr.flush()
-            os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
-    else:
-        for _ in range(args.warmup):
-            step(dev_batch)
+                self.graphed = _Outer()
+                self.note = ("cuda_graph A (fwd+loss+bwd%s+flatten) + eager NCCL all-reduce + cuda_graph B (clip+AdamW)"
+                             % (" incl. expert-parallel all-to-alls" if self.ep else ""))
+        else:
+            for _ in range(warmup):
+                step(self.dev_batch)
+
+    def run(self):
+        return self.graphed(None) if self.graphed is not None else self.eager_step(self.dev_batch)
+
+    def time_steps(self, steps, flush=None):
+        """device time of `steps` steps (CUDA events per step, L2 flushed between them outside the events), ms total"""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s_, e_ in ev:
+            if flush is not None:
+                flush()
+            s_.record()
+            self.run()
+            e_.record()
+        torch.cuda.synchronize()
+        return sum(s_.elapsed_time(e_) for s_, e_ in ev)
+
+
+EP_CAPACITY = 2.0      # rows a rank's experts may receive, in units of T*k (None = exact worst case G*T*k); overflow raises
+
+
+def make_runner(args, variant, res, B, rank, world, device, parallelism, pinned=False):
+    """TrainRunner with graph capture; expert-parallel capture failures fall back to the eager step (reported)."""
+    try:
+        return TrainRunner(variant, res, B, rank, world, device, parallelism, use_graph=not args.no_graph,
+                           warmup=args.warmup, pinned=pinned)
+    except Exception:                                # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        if parallelism != "ep":
+            raise
+        sys.stderr.write("bench.py: graph capture of the expert-parallel step failed, using the eager step\n")
+        r = TrainRunner(variant, res, B, rank, world, device, parallelism, use_graph=False, warmup=args.warmup, pinned=pinned)
+        r.note = "eager (graph capture of the expert-parallel step failed)"
+        return r
+
+
+def run_ours(args):
+    import hdmoe_b200
+    from hdmoe_b200 import _lib
+    rank, world, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    _lib.lib()     # fail loudly if the CUDA library is missing
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    hdmoe_b200.set_expert_dtype(torch.bfloat16)
+    B = args.batch
+    flush = L2Flusher(device)
+    graphed, graph_note = None, "eager"
+    try:
+        runner = make_runner(args, 1, 32, B, rank, world, device, args.parallelism, pinned=True)
+    except Exception:                            # noqa: BLE001
+        if world > 1 or args.no_graph:
+            raise
+        sys.stderr.write("bench.py: CUDA-graph capture failed, restarting in eager mode\n")
+        sys.stderr.flush()
+        os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
+    graphed, graph_note = runner.graphed, runner.note
+    host, dev_batch, step = runner.host, runner.dev_batch, runner.eager_step
     barrier(world)
     run_step = (lambda b: graphed(b)) if graphed is not None else step
     static_in = graphed.static if graphed is not None else dev_batch
@@ -333,8 +384,15 @@ def run_ours(args):
     e2e_ms = max_over_ranks(s.elapsed_time(e), world, device) / e2e_steps
     e2e_value = B * world / (e2e_ms / 1e3)
 
+    # ---- the other configurations of BASELINE.json at this N (all ranks take part): EDM sampler (configs[3], batch
+    # 1024 split over the ranks) and model_config2 at 64x64 (configs[2], batch 64 per GPU), data-parallel and expert-parallel
+    samp = cfg_c = None
+    if not args.no_sampler:
+        del runner, graphed, run_step, step
+        torch.cuda.empty_cache()
+        samp, cfg_c = scale_extras(args, rank, world, device)
     # every collective is done: release the other ranks before rank 0 measures the single-GPU extras (they must not
-    # sit in an NCCL call for a minute while rank 0 runs the sampler and the CPU baseline)
+    # sit in an NCCL call for a minute while rank 0 runs the kernel tables and the CPU baseline)
     if world > 1:
         import torch.distributed as dist
         barrier(world)
@@ -345,13 +403,6 @@ def run_ours(args):
         roof = roofline_gconv(device, peaks, flush)
         solo = world == 1                            # the sweeps, the sampler and the CPU baseline are N = 1 extras
         disp = dispatch_sweep(device, peaks, flush, full=args.full_sweep) if solo or args.full_sweep else None
-        samp = sampler_throughput(device) if solo and not args.no_sampler else None
-        cfg_c = None
-        if not args.no_sampler and solo:
-            try:
-                cfg_c = config_c_throughput(device)
-            except Exception as exc:                  # noqa: BLE001
-                cfg_c = {"error": str(exc)[:200]}
         cpu = cpu_baseline_train(sample_batch=8, iters=3) if solo else None
         ref_gpu = ref_cuda_eager(device) if solo and not args.no_sampler else None
         line = {"metric": "denoiser train img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
@@ -391,36 +442,49 @@ def _time_us(fn, flush, iters, warm=3):
 
 
 def dispatch_point(device, flush, T, E, k, D, iters=10, dtype=torch.bfloat16):
-    """permute + combine at one (tokens, experts, top-k, row width) point; algorithmic bytes per SURVEY §8d."""
+    """index build + permute + combine at one (tokens, experts, top-k, row width) point.  Algorithmic bytes per SURVEY
+    §8d: PLAN reads the router's T*k (index, weight) pairs and writes R*12 (row_src, row_expert, row_w) + T*k*4
+    (tok_rows); PERMUTE 2*R*D*s + R*4; COMBINE R*D*s + R*8 + T*D*s.  `dispatch_combine_GBs` counts all three kernels
+    sets in bytes AND time (the plan is item (2) of north_star); `permute_combine_GBs` is the data movement alone."""
     from hdmoe_b200 import ops
     gen = torch.Generator(device="cpu").manual_seed(T + E + k)
     lg = torch.randn(T, E, generator=gen) + torch.log(1.0 / torch.arange(1, E + 1).float())     # Zipf-skewed load
     idx = lg.topk(k, dim=1).indices
     sp = torch.zeros(T, E).scatter_(1, idx, 1.0 / k).to(device)
+    idx_d = idx.to(torch.int32).to(device)
+    tw_d = torch.full((T, k), 1.0 / k, device=device)
     x = torch.randn(T, D, generator=gen).to(device=device, dtype=dtype)
-    plan = ops.dispatch_plan(sp, top_k=k)
+    plan = ops.dispatch_plan_from_topk(idx_d, tw_d, E)
     rows = ops.permute(plan, x)[0]
     s = x.element_size()
     R = T * k
-    t_plan = _time_us(lambda: ops.dispatch_plan(sp, top_k=k), flush, iters)
+    t_plan = _time_us(lambda: ops.dispatch_plan_from_topk(idx_d, tw_d, E), flush, iters)
+    t_plan_dense = _time_us(lambda: ops.dispatch_plan(sp, top_k=k), flush, max(3, iters // 3))
     t_perm = _time_us(lambda: ops.permute(plan, x), flush, iters)
     t_comb = _time_us(lambda: ops.combine(rows, sp, plan), flush, iters)
+    b_plan = T * k * 8 + R * 12 + T * k * 4
     b_perm = 2 * R * D * s + R * 4
     b_comb = R * D * s + R * 8 + T * D * s
-    return {"T": T, "E": E, "k": k, "row_bytes": D * s, "plan_us": round(t_plan, 1), "permute_us": round(t_perm, 1),
-            "combine_us": round(t_comb, 1), "permute_GBs": round(b_perm / t_perm / 1e3, 1),
+    return {"T": T, "E": E, "k": k, "row_bytes": D * s, "plan_us": round(t_plan, 1), "plan_dense_us": round(t_plan_dense, 1),
+            "permute_us": round(t_perm, 1), "combine_us": round(t_comb, 1), "permute_GBs": round(b_perm / t_perm / 1e3, 1),
             "combine_GBs": round(b_comb / t_comb / 1e3, 1),
-            "dispatch_combine_GBs": round((b_perm + b_comb) / (t_perm + t_comb) / 1e3, 1)}
+            "permute_combine_GBs": round((b_perm + b_comb) / (t_perm + t_comb) / 1e3, 1),
+            "dispatch_combine_GBs": round((b_plan + b_perm + b_comb) / (t_plan + t_perm + t_comb) / 1e3, 1)}
 
 
 def dispatch_sweep(device, peaks, flush, full=False):
-    pts = [(1024, 4, 1, 32768), (1024, 8, 2, 32768), (65536, 16, 2, 512), (262144, 64, 2, 128), (1048576, 64, 1, 128)]
+    pts = [(1024, 4, 1, 32768), (1024, 8, 2, 32768), (65536, 16, 2, 512), (262144, 64, 2, 128), (1048576, 64, 1, 128),
+           (1048576, 64, 2, 512)]
     if full:
         pts = [(T, E, k, D) for T in (4096, 16384, 65536, 262144, 1048576) for E in (4, 8, 16, 32, 64) for k in (1, 2)
                for D in (32, 128, 512) if T * k * D * 2 <= (4 << 30)] + [(256, 4, 1, 32768), (1024, 4, 1, 32768)]
     out = [dispatch_point(device, flush, *p) for p in pts]
     best = max(o["dispatch_combine_GBs"] for o in out)
-    return {"unit": "GB/s", "peak": peaks["hbm"], "best_frac": round(best / peaks["hbm"], 4), "points": out}
+    ref = out[-1] if full else out[0]            # the reference-faithful point (T = 1024 samples, 64 KiB bf16 rows)
+    return {"unit": "GB/s", "peak": peaks["hbm"], "best_frac": round(best / peaks["hbm"], 4),
+            "reference_point_frac": round(ref["dispatch_combine_GBs"] / peaks["hbm"], 4),
+            "note": "dispatch_combine_GBs = (plan + permute + combine bytes) / (plan + permute + combine time); L2 flushed "
+                    "(256 MiB write) before every timed launch", "points": out}
 
 
 # Every MP_Conv of one Unet_expert that runs through the grouped tcgen05 kernels (SURVEY Appendix D, cfg1/cfg2 at 32x32):
@@ -566,80 +630,80 @@ def ncu_traffic(kernel):
     return json.load(open(p)).get(kernel)
 
 
-def sampler_throughput(device, B=1024, steps=18):
-    """EDM Heun sampler, 18 steps / 35 NFE, model_config2, CLIP-shaped text (BASELINE.json configs[3])."""
+def sampler_throughput(device, rank, world, total_batch=1024, steps=18, guidance=1.0):
+    """EDM Heun sampler, 18 steps / 35 NFE (70 with guidance), model_config2, CLIP-shaped text (BASELINE.json configs[3]):
+    the batch of 1024 is split over the ranks (samples are independent: no collective), time = max over ranks."""
     import hdmoe_b200
+    B = max(1, total_batch // world)
     model = build_model(2, device)
     model.eval()
-    gen = torch.Generator().manual_seed(SEED)
+    gen = torch.Generator().manual_seed(SEED + rank)
     noise = torch.randn(B, 4, 32, 32, generator=gen).to(device)
     text = torch.randn(B, 77, 768, generator=gen).to(device)
-    smp = hdmoe_b200.EDM_Sampler(model, model, num_solve_steps=steps, guidance=1.0, use_cuda_graph=True)
-    smp.sample(noise, text, P_MEAN, P_STD)               # warm-up: allocator, autotune, graph capture
-    torch.cuda.synchronize()
+    uncond = torch.zeros_like(text) if guidance != 1.0 else None
+    smp = hdmoe_b200.EDM_Sampler(model, model, num_solve_steps=steps, guidance=guidance, use_cuda_graph=True)
+    smp.sample(noise, text, P_MEAN, P_STD, uncond_text_emb=uncond)      # warm-up: allocator, graph capture
+    barrier(world)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     smp.nfe = 0
     a.record()
-    out = smp.sample(noise, text, P_MEAN, P_STD)
+    out = smp.sample(noise, text, P_MEAN, P_STD, uncond_text_emb=uncond)
     b.record()
     torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    return {"metric": "EDM sample img/s", "value": round(B / (ms / 1e3), 1), "unit": "img/s", "batch": B, "nfe": smp.nfe,
-            "ms": round(ms, 1), "finite": bool(torch.isfinite(out).all()),
-            "execution": "one CUDA graph per denoiser evaluation, fused Heun kernels between"}
+    ms = max_over_ranks(a.elapsed_time(b), world, device)
+    fin = bool(torch.isfinite(out).all())
+    del smp, model
+    torch.cuda.empty_cache()
+    return {"metric": "EDM sample img/s", "value": round(B * world / (ms / 1e3), 1), "unit": "img/s", "batch": B * world,
+            "batch_per_gpu": B, "nfe": (2 * steps - 1) * (2 if guidance != 1.0 else 1), "guidance": guidance,
+            "ms": round(ms, 1), "finite": fin,
+            "execution": "one CUDA graph per denoiser evaluation, fused Heun kernels between; ranks sample independently"}
 
 
-def config_c_throughput(device, B=64, steps=5):
-    """BASELINE configs[2] on ONE GPU: model_config2 at 4x64x64 (11.2 M parameters), bf16 expert path, whole train step
-    (fwd + EDM_LOSS + bwd + clip + AdamW) captured in a CUDA graph, batch 64."""
+def config_c_throughput(args, rank, world, device, parallelism, B=64, steps=5):
+    """BASELINE configs[2]: model_config2 at 4x64x64 (11.2 M parameters), bf16 expert path, batch 64 per GPU, whole train
+    step; "dp" = data-parallel replicas, "ep" = U-Net experts sharded over the ranks (static-shape all-to-all layer)."""
+    from hdmoe_b200 import expert_parallel as EP
     import hdmoe_b200
-    from hdmoe_b200.utils import EDM_LOSS
-    from hdmoe_b200.train_step import GraphedTrainStep
-    torch.manual_seed(0)
-    model = hdmoe_b200.model_config2.preconditioned_HDMOEM(**dict(FULL, IN_img_resolution=64))
-    gen = torch.Generator().manual_seed(100)
-    with torch.no_grad():
-        for p in model.parameters():
-            if float(p.abs().max()) == 0:
-                p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
-    model.to(device).train()
-    crit = EDM_LOSS(**LOSS)
-    params = list(model.parameters())
-    from hdmoe_b200.optim import FusedAdamW
-    opt = FusedAdamW(params, lr=5e-4, max_grad_norm=1.0)
-    b = {k: v.to(device) for k, v in synth_batch(B, 64, 0, device).items()}
-
-    def step(b):
-        out = model(x=b["x"], sigma=b["sigma"], text_emb=b["text"], Unet_router_mask=b["um"], Vit_router_mask=b["vm"],
-                    zeta=2.0, transition_point=P_MEAN, softness=P_STD, return_log_var=True)
-        loss = crit(b["sigma"], b["x0"], b["sigma"], out)["loss"]
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return loss
-
-    mode = "cuda_graph"
     try:
-        g = GraphedTrainStep(step, b, warmup=3).capture()
-        run = lambda: g(None)
+        r = make_runner(args, 2, 64, B, rank, world, device, parallelism)
+        r.run()
+        barrier(world)
+        ms = max_over_ranks(r.time_steps(steps), world, device) / steps
+        loss = r.run()
+        fin = bool(torch.isfinite(loss).all())
+        if parallelism == "ep":
+            EP.check_overflow()
+        note = r.note
+        del r
     except Exception as exc:                          # noqa: BLE001
-        mode = "eager (graph capture failed: %s)" % str(exc)[:80]
-        run = lambda: step(b)
-        for _ in range(3):
-            run()
-    run()
-    torch.cuda.synchronize()
-    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
-        loss = run()
-    c.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(c) / steps
-    del model, opt
-    return {"metric": "denoiser train img/s", "workload": "model_config2 4x64x64 train step, batch %d, 1 GPU" % B,
-            "value": round(B / (ms / 1e3), 1), "unit": "img/s", "ms_per_step": round(ms, 2), "execution": mode,
-            "finite": bool(torch.isfinite(loss).all())}
+        import traceback
+        traceback.print_exc()
+        hdmoe_b200.disable_expert_parallel()
+        torch.cuda.empty_cache()
+        return {"parallelism": parallelism, "error": str(exc)[:300]}
+    hdmoe_b200.disable_expert_parallel()
+    torch.cuda.empty_cache()
+    return {"metric": "denoiser train img/s", "workload": "model_config2 4x64x64 train step, batch %d per GPU" % B,
+            "parallelism": (f"ep{world} (U-Net experts) + dp{world} (trunk)" if parallelism == "ep" else f"dp{world}"),
+            "value": round(B * world / (ms / 1e3), 1), "unit": "img/s", "ms_per_step": round(ms, 2), "execution": note,
+            "finite": fin}
+
+
+def scale_extras(args, rank, world, device):
+    """(sampler, config_c) records of this N; every rank runs them (rank 0 reports)."""
+    samp = {"g1": sampler_throughput(device, rank, world, guidance=1.0)}
+    samp["g2"] = sampler_throughput(device, rank, world, guidance=2.0)
+    samp.update({k: samp["g1"][k] for k in ("metric", "value", "unit", "batch", "nfe", "ms", "finite")})   # headline: g = 1
+    cfg_c = {"dp": config_c_throughput(args, rank, world, device, "dp")}
+    if world > 1:
+        cfg_c["ep"] = config_c_throughput(args, rank, world, device, "ep")
+        try:
+            cfg_c["ep_over_dp"] = round(cfg_c["ep"]["value"] / cfg_c["dp"]["value"], 3)
+        except (KeyError, ZeroDivisionError):
+            pass
+    cfg_c.update({k: cfg_c["dp"].get(k) for k in ("metric", "value", "unit", "ms_per_step", "workload")})
+    return samp, cfg_c
 
 
 # ---------------------------------------------------------------------------------------------------------

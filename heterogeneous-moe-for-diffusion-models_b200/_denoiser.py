@@ -106,20 +106,22 @@ def set_fused_glue(enabled: bool) -> None:
 
 
 # expert parallelism for the U-Net MoE layer; None = every rank runs all experts (pure DP)
-_EP = {"placement": None, "group": None}
+_EP = {"placement": None, "group": None, "capacity_factor": None}
 
 
-def enable_expert_parallel(kernel_sizes=None, group=None, placement=None) -> None:
-    """Shard the U-Net experts over the ranks of `group` (cost-balanced); ViT experts stay replicated."""
+def enable_expert_parallel(kernel_sizes=None, group=None, placement=None, capacity_factor=None) -> None:
+    """Shard the U-Net experts over the ranks of `group` (cost-balanced); ViT experts stay replicated.
+    capacity_factor: rows a rank's experts may receive per layer in units of T*k (None = exact worst case, G*T*k);
+    an overflow sets a device flag that expert_parallel.check_overflow() raises on."""
     import torch.distributed as dist
     from . import expert_parallel as EP
     if placement is None:
         placement = EP.ExpertPlacement.balanced(EP.unet_expert_costs(kernel_sizes), dist.get_world_size(group))
-    _EP["placement"], _EP["group"] = placement, group
+    _EP["placement"], _EP["group"], _EP["capacity_factor"] = placement, group, capacity_factor
 
 
 def disable_expert_parallel() -> None:
-    _EP["placement"] = _EP["group"] = None
+    _EP["placement"] = _EP["group"] = _EP["capacity_factor"] = None
 
 
 def _run_experts_on_rows(experts, plan, xr, tr, txr, nhwc_out: bool = False):
@@ -202,9 +204,11 @@ def _run_experts_on_rows(experts, plan, xr, tr, txr, nhwc_out: bool = False):
 
 def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: torch.Tensor,
                            time_emb: torch.Tensor, text_emb: Optional[torch.Tensor],
-                           top_k: Optional[int] = None, nhwc_out: bool = False) -> torch.Tensor:
+                           top_k: Optional[int] = None, nhwc_out: bool = False, topk=None) -> torch.Tensor:
     """One MoE layer: same signature and result as the reference helper (models/model_config2.py:11-39).
     `nhwc_out` (B200 extra, used by HDMOEM's channels-last tail): the result comes back as [B, H, W, C].
+    `topk` (B200 extra): the router kernel's (topk_idx, topk_w) of `out_router`; the plan is then built from these
+    T*k pairs instead of two passes over the dense [T, E] matrix (same criterion on the same values: identical plan).
 
     dispatch plan (bit-exact, expert-major / token-ascending, criterion weight > 0) -> ONE fused gather of
     the image rows, time rows and mean-pooled text rows -> experts on contiguous row ranges -> ONE
@@ -221,9 +225,12 @@ def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: 
             return _run_experts_on_rows([experts[i] for i in local_ids], lplan, xr_, tr_, txr_)
 
         out = EP.ep_moe_layer(x, out_router, time_emb, text_emb, run_local, _EP["placement"], k, group=_EP["group"],
-                              payload_dtype=dt)
+                              payload_dtype=dt, capacity_factor=_EP["capacity_factor"])
         return out.permute(0, 2, 3, 1).contiguous() if nhwc_out else out
-    plan = ops.dispatch_plan(out_router, top_k)
+    if topk is not None and topk[0].shape[0] == out_router.shape[0]:
+        plan = ops.dispatch_plan_from_topk(topk[0], topk[1], out_router.shape[1])
+    else:
+        plan = ops.dispatch_plan(out_router, top_k)
     srcs = [x.to(dt), time_emb.to(dt)] + ([text_emb.to(dt)] if text_emb is not None else [])
     rows = ops.permute(plan, *srcs)
     xr, tr = rows[0], rows[1]
@@ -307,6 +314,14 @@ class HDMOEM(nn.Module):
         return self._forward_body(x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point,
                                   softness, alpha_routing, noise)
 
+    @staticmethod
+    def _topk_of(router, x):
+        """(topk_idx, topk_w) the router's fused gate kernel produced in this forward (CUDA path only)."""
+        last = getattr(router, "last", None)
+        if not x.is_cuda or not last:
+            return None
+        return last["topk_idx"], last["topk_w"]
+
     def _router_trunk(self, x):
         """The grouped tcgen05 trunk runner of the two routers, or None when the configuration does not use it (fp32
         expert path, CPU tensors, unsupported shapes, switched off)."""
@@ -353,18 +368,23 @@ class HDMOEM(nn.Module):
                                                         noise=noise.get("vit"), pooled=pool_vit)
             w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
                                                   noise=noise.get("unet"), pooled=pool_un)
-            out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k, nhwc_out=glue)
+            tk_u, tk_v = self._topk_of(self.Unet_router, x), self._topk_of(self.vit_router, x)
+            out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k, nhwc_out=glue,
+                                           topk=tk_u)
             with torch.cuda.stream(fk.s):
                 out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k,
-                                               nhwc_out=glue)
+                                               nhwc_out=glue, topk=tk_v)
             fk.join(w_vit, p_vit, raw_vit, out_v)
         else:
             w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
                                                     noise=noise.get("vit"), pooled=pool_vit)
             w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
                                                   noise=noise.get("unet"), pooled=pool_un)
-            out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k, nhwc_out=glue)
-            out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k, nhwc_out=glue)
+            tk_u, tk_v = self._topk_of(self.Unet_router, x), self._topk_of(self.vit_router, x)
+            out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k, nhwc_out=glue,
+                                           topk=tk_u)
+            out_v = router_to_unet_experts(in_vit, self.VIT_experts, w_vit, te, text_emb, top_k=self.top_k, nhwc_out=glue,
+                                           topk=tk_v)
         if glue:
             # channels-last tail: out_u / out_v are [B, H, W, C]; swap (cfg1) and the whole text-blend / gate / mix chain
             # are one fused kernel each (csrc/trunk_glue.cu); output_proj reads the mix through a channels-last view

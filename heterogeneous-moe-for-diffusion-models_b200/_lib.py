@@ -43,6 +43,7 @@ PROTOTYPES = {
     "hdmoe_router_gate_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "hdmoe_dispatch_plan_workspace_bytes": (_sz, [_i, _i]),
     "hdmoe_dispatch_plan": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hdmoe_dispatch_plan_topk": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hdmoe_permute_rows": (_i, [_p, _p, _p, _i, _p, _p, _i, _p]),
     "hdmoe_combine_rows": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i64, _p]),
     "hdmoe_combine_rows_bwd": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i64, _p, _p, _p]),

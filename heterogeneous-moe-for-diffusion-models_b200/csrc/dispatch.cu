@@ -11,8 +11,9 @@ namespace hdmoe {
 
 // ---------------------------------------------------------------------------------------------------
 // Dispatch plan.  Stable counting sort of the (token, expert) pairs with sparse_w > 0 by expert.
-//   pass 1 (count)   : per 256-token tile, per-expert counts -> tilecnt[e][tile]
+//   pass 1 (count)   : per tile (G groups of 256 tokens), per-expert counts -> tilecnt[e][tile]
 //   pass 2 (scan)    : exclusive scan over the expert-major (e, tile) array -> tileoff, counts, offsets
+//                      (one CTA, coalesced 4096-element blocks with a running carry; <= 1024 tiles)
 //   pass 3 (scatter) : ballot ranks inside the tile give each pair its row; writes row_src / row_expert /
 //                      row_w / tok_rows.
 // One thread owns one token and keeps its E selection flags in a 64-bit register mask.
@@ -54,61 +55,131 @@ __device__ __forceinline__ unsigned long long token_mask(const float* __restrict
     return threadIdx.x < ntok ? v : 0ull;
 }
 
+// Selection source of the plan kernels: the dense [T, E] sparse-weight matrix (the reference helper's argument), or the
+// router kernel's own top-k output (topk_idx / topk_w [T, K], T*K*8 bytes instead of two passes over T*E*4).
+struct PlanSrc {
+    const float* dense;          // [T, E] or NULL
+    const int32_t* topk_idx;     // [T, K]
+    const float* topk_w;         // [T, K]
+    int K;
+};
+
+// One thread = one token of the current 256-token group: its E selection flags (criterion weight > 0, quirk Q3) and, for
+// the top-k source, the (index, weight) pairs in registers.
+struct TokSel {
+    unsigned long long mask;
+    int32_t idx[HDMOE_MAX_TOPK];
+    float w[HDMOE_MAX_TOPK];
+};
+
+__device__ __forceinline__ void token_select(const PlanSrc& src, int group, int T, int E, uint32_t* bits, TokSel& ts) {
+    if (src.dense) {
+        ts.mask = token_mask(src.dense, group, T, E, bits);
+        return;
+    }
+    const int t = group * kPlanThreads + threadIdx.x;
+    ts.mask = 0ull;
+#pragma unroll
+    for (int k = 0; k < HDMOE_MAX_TOPK; ++k) {
+        ts.idx[k] = -1;
+        ts.w[k] = 0.f;
+        if (k < src.K && t < T) {
+            const int e = src.topk_idx[(size_t)t * src.K + k];
+            const float v = src.topk_w[(size_t)t * src.K + k];
+            ts.idx[k] = e;
+            ts.w[k] = v;
+            if (v > 0.f && e >= 0 && e < E) ts.mask |= 1ull << e;      // NaN > 0 is false: all-masked rows dispatch nothing
+        }
+    }
+}
+
+// tile = G consecutive 256-token groups handled by one CTA (G keeps the (expert, tile) scan array small at T ~ 1 M)
+// per-expert counts of tile `tile` into cnt[] (shared)
+__device__ __forceinline__ void plan_count_tile(const PlanSrc& src, int T, int E, int tile, int G, int* cnt, uint32_t* bits) {
+    if (threadIdx.x < E) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int ngroups = (T + kPlanThreads - 1) / kPlanThreads;
+    for (int g = tile * G; g < min((tile + 1) * G, ngroups); ++g) {
+        TokSel ts;
+        token_select(src, g, T, E, bits, ts);
+        if (src.K == 1 && !src.dense) {
+            // one expert per token: the lanes of a warp that chose the same expert find each other with one match
+            const int e = ts.mask ? ts.idx[0] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, e >= 0 ? e : 64 + lane);
+            if (e >= 0 && lane == __ffs(peers) - 1) atomicAdd(&cnt[e], __popc(peers));
+        } else {
+            // only the experts some lane of this warp selected (<= 32 * K of the E columns)
+            unsigned p_lo = __reduce_or_sync(0xffffffffu, (unsigned)ts.mask);
+            unsigned p_hi = __reduce_or_sync(0xffffffffu, (unsigned)(ts.mask >> 32));
+            for (unsigned long long present = ((unsigned long long)p_hi << 32) | p_lo; present; present &= present - 1) {
+                const int e = __ffsll((long long)present) - 1;
+                const unsigned b = __ballot_sync(0xffffffffu, (ts.mask >> e) & 1ull);
+                if (lane == 0) atomicAdd(&cnt[e], __popc(b));
+            }
+        }
+        __syncthreads();       // bits[] is reused by the next group
+    }
+}
+
 __global__ void __launch_bounds__(kPlanThreads)
-plan_count_kernel(const float* __restrict__ w, int T, int E, int ntiles, int32_t* __restrict__ tilecnt) {
+plan_count_kernel(PlanSrc src, int T, int E, int ntiles, int G, int32_t* __restrict__ tilecnt) {
     __shared__ int cnt[HDMOE_MAX_EXPERTS];
     __shared__ uint32_t bits[kPlanThreads * HDMOE_MAX_EXPERTS / 32 + 2];
-    if (threadIdx.x < E) cnt[threadIdx.x] = 0;
-    const unsigned long long m = token_mask(w, blockIdx.x, T, E, bits);   // contains a __syncthreads
-    const int lane = threadIdx.x & 31;
-    for (int e = 0; e < E; ++e) {
-        const unsigned b = __ballot_sync(0xffffffffu, (m >> e) & 1ull);
-        if (lane == 0 && b) atomicAdd(&cnt[e], __popc(b));
-    }
-    __syncthreads();
+    plan_count_tile(src, T, E, blockIdx.x, G, cnt, bits);
     if (threadIdx.x < E) tilecnt[(size_t)threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// single block, 1024 threads: exclusive scan of n = E*ntiles ints (expert-major)
+// single block, 1024 threads: exclusive scan of n = E*ntiles ints (expert-major), streamed in coalesced blocks of 4096
+// with a running carry (the round-1 version gave every thread a private contiguous range: uncoalesced, 657 us at T = 1 M)
 __global__ void __launch_bounds__(1024)
 plan_scan_kernel(const int32_t* __restrict__ tilecnt, int E, int ntiles, int cap, int32_t* __restrict__ tileoff,
                  int32_t* __restrict__ counts, int32_t* __restrict__ offsets, int32_t* __restrict__ status) {
     __shared__ int wsum[32];
     __shared__ int carry_s;
     const int n = E * ntiles;
-    const int per = (n + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(lo + per, n);
-    int s = 0;
-    for (int i = lo; i < hi; ++i) s += tilecnt[i];
-    // block exclusive scan of s
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int incl = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) wsum[warp] = incl;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    if (warp == 0) {
-        int v = wsum[lane], iv = v;
+    for (int base = 0; base < n; base += 4096) {
+        const int carry = carry_s;       // stable here: written only between the two barriers below
+        const int i0 = base + threadIdx.x * 4;
+        int v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = i0 + q < n ? tilecnt[i0 + q] : 0;
+        const int s = v[0] + v[1] + v[2] + v[3];
+        int incl = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int u = __shfl_up_sync(0xffffffffu, iv, o);
-            if (lane >= o) iv += u;
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
         }
-        wsum[lane] = iv - v;
-        if (lane == 31) carry_s = iv;
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = wsum[lane];
+            int iw = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, iw, o);
+                if (lane >= o) iw += u;
+            }
+            wsum[lane] = iw - w;                     // exclusive warp offsets
+            if (lane == 31) carry_s = carry + iw;    // total so far (read again only after the next barrier)
+        }
+        __syncthreads();
+        int run = carry + wsum[warp] + incl - s;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q;
+            if (i < n) {
+                tileoff[i] = run;
+                if (i % ntiles == 0) offsets[i / ntiles] = run;
+                run += v[q];
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    int run = wsum[warp] + incl - s;
-    for (int i = lo; i < hi; ++i) {
-        const int c = tilecnt[i];
-        tileoff[i] = run;
-        if (i % ntiles == 0) offsets[i / ntiles] = run;
-        run += c;
-    }
-    __syncthreads();
     if (threadIdx.x == 0) {
         offsets[E] = carry_s;
         status[0] = carry_s > cap ? 1 : 0;
@@ -117,48 +188,140 @@ plan_scan_kernel(const int32_t* __restrict__ tilecnt, int E, int ntiles, int cap
     if (threadIdx.x < E) counts[threadIdx.x] = offsets[threadIdx.x + 1] - offsets[threadIdx.x];
 }
 
+// rows of tile `tile`; run_s[e] (shared) = first free row of expert e for this tile on entry
+__device__ __forceinline__ void plan_scatter_tile(const PlanSrc& src, int T, int E, int tile, int G, int cap, int K,
+                                                  int32_t* __restrict__ row_src, int32_t* __restrict__ row_expert,
+                                                  float* __restrict__ row_w, int32_t* __restrict__ tok_rows,
+                                                  int32_t* __restrict__ status, int (*warpoff)[HDMOE_MAX_EXPERTS],
+                                                  int* run_s, uint32_t* bits) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ngroups = (T + kPlanThreads - 1) / kPlanThreads;
+    for (int g = tile * G; g < min((tile + 1) * G, ngroups); ++g) {
+        const int t = g * kPlanThreads + threadIdx.x;
+        TokSel ts;
+        token_select(src, g, T, E, bits, ts);
+        const bool one = src.K == 1 && !src.dense;
+        for (int e = lane; e < E; e += 32) warpoff[warp][e] = 0;
+        __syncwarp();
+        unsigned peers1 = 0;
+        unsigned long long present = 0ull;
+        if (one) {
+            const int e = ts.mask ? ts.idx[0] : -1;
+            peers1 = __match_any_sync(0xffffffffu, e >= 0 ? e : 64 + lane);
+            if (e >= 0 && lane == __ffs(peers1) - 1) warpoff[warp][e] = __popc(peers1);
+        } else {
+            const unsigned p_lo = __reduce_or_sync(0xffffffffu, (unsigned)ts.mask);
+            const unsigned p_hi = __reduce_or_sync(0xffffffffu, (unsigned)(ts.mask >> 32));
+            present = ((unsigned long long)p_hi << 32) | p_lo;
+            for (unsigned long long pr = present; pr; pr &= pr - 1) {
+                const int e = __ffsll((long long)pr) - 1;
+                const unsigned b = __ballot_sync(0xffffffffu, (ts.mask >> e) & 1ull);
+                if (lane == 0) warpoff[warp][e] = __popc(b);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < E) {   // exclusive scan over warps, per expert, seeded with the running offset of the tile
+            int run = run_s[threadIdx.x];
+            for (int wv = 0; wv < kPlanThreads / 32; ++wv) {
+                const int c = warpoff[wv][threadIdx.x];
+                warpoff[wv][threadIdx.x] = run;
+                run += c;
+            }
+            run_s[threadIdx.x] = run;
+        }
+        __syncthreads();
+        int slot = 0;
+        // ascending expert order over the experts present in this warp (uniform loop: every lane takes part in the ballot)
+        unsigned long long walk = one ? 0ull : present;
+        bool one_pending = one;
+        while (walk || one_pending) {
+            int e;
+            bool sel;
+            unsigned b;
+            if (one_pending) {
+                one_pending = false;
+                e = ts.mask ? ts.idx[0] : 0;
+                sel = ts.mask != 0ull;
+                b = peers1;
+            } else {
+                e = __ffsll((long long)walk) - 1;
+                walk &= walk - 1;
+                sel = (ts.mask >> e) & 1ull;
+                b = __ballot_sync(0xffffffffu, sel);
+            }
+            if (sel) {
+                const int pos = warpoff[warp][e] + __popc(b & ((1u << lane) - 1u));
+                if (pos < cap) {
+                    float wv = 0.f;
+                    if (src.dense) {
+                        wv = src.dense[(size_t)t * E + e];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < HDMOE_MAX_TOPK; ++k)
+                            if (ts.idx[k] == e) wv = ts.w[k];
+                    }
+                    row_src[pos] = t;
+                    row_expert[pos] = e;
+                    row_w[pos] = wv;
+                }
+                if (slot < K) tok_rows[(size_t)t * K + slot] = pos < cap ? pos : -1;
+                else status[0] = 2;
+                ++slot;
+            }
+        }
+        if (t < T)
+            for (; slot < K; ++slot) tok_rows[(size_t)t * K + slot] = -1;
+        __syncthreads();       // warpoff / bits are rewritten by the next group
+    }
+}
+
 __global__ void __launch_bounds__(kPlanThreads)
-plan_scatter_kernel(const float* __restrict__ w, int T, int E, int ntiles, int cap, int K,
+plan_scatter_kernel(PlanSrc src, int T, int E, int ntiles, int G, int cap, int K,
                     const int32_t* __restrict__ tileoff, int32_t* __restrict__ row_src,
                     int32_t* __restrict__ row_expert, float* __restrict__ row_w, int32_t* __restrict__ tok_rows,
                     int32_t* __restrict__ status) {
     __shared__ int warpoff[kPlanThreads / 32][HDMOE_MAX_EXPERTS];
+    __shared__ int run_s[HDMOE_MAX_EXPERTS];         // next free row of every expert inside this tile
     __shared__ uint32_t bits[kPlanThreads * HDMOE_MAX_EXPERTS / 32 + 2];
-    const int t = blockIdx.x * kPlanThreads + threadIdx.x;
-    const unsigned long long m = token_mask(w, blockIdx.x, T, E, bits);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int e = 0; e < E; ++e) {
-        const unsigned b = __ballot_sync(0xffffffffu, (m >> e) & 1ull);
-        if (lane == 0) warpoff[warp][e] = __popc(b);
+    if (threadIdx.x < E) run_s[threadIdx.x] = tileoff[(size_t)threadIdx.x * ntiles + blockIdx.x];
+    __syncthreads();
+    plan_scatter_tile(src, T, E, blockIdx.x, G, cap, K, row_src, row_expert, row_w, tok_rows, status, warpoff, run_s, bits);
+}
+
+// T <= kPlanSmallT: the whole plan (count, offsets, scatter, tail fill) in ONE CTA -- at the reference's own sizes
+// (T = batch = 256 ... 1024) the four-launch version is pure launch latency (19 us against 30 us of data movement)
+constexpr int kPlanSmallT = 4096;
+__global__ void __launch_bounds__(kPlanThreads)
+plan_small_kernel(PlanSrc src, int T, int E, int cap, int K, int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
+                  int32_t* __restrict__ row_src, int32_t* __restrict__ row_expert, float* __restrict__ row_w,
+                  int32_t* __restrict__ tok_rows, int32_t* __restrict__ status) {
+    __shared__ int warpoff[kPlanThreads / 32][HDMOE_MAX_EXPERTS];
+    __shared__ int run_s[HDMOE_MAX_EXPERTS];
+    __shared__ int cnt[HDMOE_MAX_EXPERTS];
+    __shared__ uint32_t bits[kPlanThreads * HDMOE_MAX_EXPERTS / 32 + 2];
+    __shared__ int total_s;
+    const int G = (T + kPlanThreads - 1) / kPlanThreads;
+    if (threadIdx.x == 0) status[0] = 0;
+    plan_count_tile(src, T, E, 0, G, cnt, bits);
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int e = 0; e < E; ++e) {
+            offsets[e] = run;
+            run_s[e] = run;
+            counts[e] = cnt[e];
+            run += cnt[e];
+        }
+        offsets[E] = run;
+        total_s = run;
+        if (run > cap) status[0] = 1;
     }
     __syncthreads();
-    if (threadIdx.x < E) {   // exclusive scan over warps, per expert, seeded with the tile's global offset
-        int run = tileoff[(size_t)threadIdx.x * ntiles + blockIdx.x];
-        for (int wv = 0; wv < kPlanThreads / 32; ++wv) {
-            const int c = warpoff[wv][threadIdx.x];
-            warpoff[wv][threadIdx.x] = run;
-            run += c;
-        }
+    plan_scatter_tile(src, T, E, 0, G, cap, K, row_src, row_expert, row_w, tok_rows, status, warpoff, run_s, bits);
+    for (int i = total_s + threadIdx.x; i < cap; i += kPlanThreads) {
+        row_src[i] = -1;
+        row_expert[i] = -1;
+        row_w[i] = 0.f;
     }
-    __syncthreads();
-    int slot = 0;
-    for (int e = 0; e < E; ++e) {
-        const bool sel = (m >> e) & 1ull;
-        const unsigned b = __ballot_sync(0xffffffffu, sel);
-        if (sel) {
-            const int pos = warpoff[warp][e] + __popc(b & ((1u << lane) - 1u));
-            if (pos < cap) {
-                row_src[pos] = t;
-                row_expert[pos] = e;
-                row_w[pos] = w[(size_t)t * E + e];
-            }
-            if (slot < K) tok_rows[(size_t)t * K + slot] = pos < cap ? pos : -1;
-            else status[0] = 2;
-            ++slot;
-        }
-    }
-    if (t < T)
-        for (; slot < K; ++slot) tok_rows[(size_t)t * K + slot] = -1;
 }
 
 // fills the unused tail [R, cap) so that fixed-size consumers see well-defined values
@@ -250,7 +413,8 @@ permute_bulk_kernel(PermuteArgs a, const int32_t* __restrict__ row_src, const in
         const long long rem = a.row_bytes[i] - off;
         bytes = (uint32_t)(rem < kChunk ? rem : kChunk);
         dst = a.dst[i] + (long long)r * a.row_bytes[i] + off;
-        src = r < R ? a.src[i] + (long long)row_src[r] * a.row_bytes[i] + off : nullptr;   // tail rows: zero-fill
+        const int sr = r < R ? row_src[r] : -1;                 // tail rows and holes (row_src < 0): zero-fill
+        src = sr >= 0 ? a.src[i] + (long long)sr * a.row_bytes[i] + off : nullptr;
     };
     auto load = [&](long long k) {
         const int s = (int)(k % kBulkStages);
@@ -310,8 +474,9 @@ permute_vec16_kernel(PermuteArgs a, const int32_t* __restrict__ row_src, const i
                 else if (a.n_tensors > 2 && c >= vb2) { i = 2; c -= vb2; }
                 else if (a.n_tensors > 1 && c >= vb1) { i = 1; c -= vb1; }
                 dstp[q] = reinterpret_cast<int4*>(a.dst[i] + (long long)r * a.row_bytes[i]) + c;
-                if (r < R)
-                    val[q] = ld_stream(reinterpret_cast<const int4*>(a.src[i] + (long long)row_src[r] * a.row_bytes[i]) + c);
+                const int sr = r < R ? row_src[r] : -1;
+                if (sr >= 0)
+                    val[q] = ld_stream(reinterpret_cast<const int4*>(a.src[i] + (long long)sr * a.row_bytes[i]) + c);
             }
         }
 #pragma unroll
@@ -341,8 +506,9 @@ permute_vec_kernel(PermuteArgs a, const int32_t* __restrict__ row_src, const int
         const long long rem = a.row_bytes[i] - off;
         const int bytes = (int)(rem < kVecPiece ? rem : kVecPiece);
         char* dst = a.dst[i] + (long long)r * a.row_bytes[i] + off;
-        const bool live = r < R;
-        const char* src = live ? a.src[i] + (long long)row_src[r] * a.row_bytes[i] + off : nullptr;
+        const int sr = r < R ? row_src[r] : -1;
+        const bool live = sr >= 0;               // tail rows and holes (row_src < 0) are zero-filled
+        const char* src = live ? a.src[i] + (long long)sr * a.row_bytes[i] + off : nullptr;
         const bool al16 = ((((uintptr_t)dst) | ((uintptr_t)(live ? src : dst)) | (uintptr_t)bytes) & 15) == 0;
         if (al16) {
             const int n16 = bytes >> 4;
@@ -470,7 +636,7 @@ combine_bwd_kernel(const TR* __restrict__ rows, const TY* __restrict__ dY, const
     const int R = min(*n_rows_dev, cap);
     for (int r = blockIdx.x; r < cap; r += gridDim.x) {
         TR* dr = d_rows + (long long)r * D;
-        if (r >= R) {
+        if (r >= R || row_src[r] < 0) {          // unused tail rows and holes of a spread (expert-parallel) layout
             for (long long d = (long long)threadIdx.x << 2; d < D; d += (long long)blockDim.x << 2)
                 Vec4<TR>::store(dr + d, make_float4(0.f, 0.f, 0.f, 0.f));
             continue;
@@ -506,33 +672,67 @@ combine_bwd_kernel(const TR* __restrict__ rows, const TY* __restrict__ dY, const
 
 using namespace hdmoe;
 
+// groups of 256 tokens per CTA: keep the (expert, tile) scan array at <= 1024 tiles
+static int plan_groups_per_tile(int T) {
+    const int ngroups = (T + kPlanThreads - 1) / kPlanThreads;
+    return (ngroups + 1023) / 1024;
+}
+
 extern "C" size_t hdmoe_dispatch_plan_workspace_bytes(int T, int E) {
     const size_t ntiles = (size_t)(T + kPlanThreads - 1) / kPlanThreads + 1;
     return 2 * ntiles * (size_t)E * sizeof(int32_t) + 64;
 }
 
-extern "C" int hdmoe_dispatch_plan(const float* sparse_w, int T, int E, int cap, int K, int32_t* counts,
-                                   int32_t* offsets, int32_t* row_src, int32_t* row_expert, float* row_w,
-                                   int32_t* tok_rows, int32_t* status, void* workspace, hdmoe_stream_t stream) {
+static int dispatch_plan_impl(PlanSrc src, int T, int E, int cap, int K, int32_t* counts, int32_t* offsets,
+                              int32_t* row_src, int32_t* row_expert, float* row_w, int32_t* tok_rows, int32_t* status,
+                              void* workspace, hdmoe_stream_t stream) {
     HDMOE_CHECK_ARG(T >= 1 && E >= 1 && E <= HDMOE_MAX_EXPERTS, "dispatch_plan: need T >= 1, 1 <= E <= %d",
                     HDMOE_MAX_EXPERTS);
     HDMOE_CHECK_ARG(cap >= 1 && K >= 1 && K <= E, "dispatch_plan: need cap >= 1 and 1 <= K <= E");
-    HDMOE_CHECK_ARG(sparse_w && counts && offsets && row_src && row_expert && row_w && tok_rows && status && workspace,
+    HDMOE_CHECK_ARG(counts && offsets && row_src && row_expert && row_w && tok_rows && status && workspace,
                     "dispatch_plan: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const int ntiles = (T + kPlanThreads - 1) / kPlanThreads;
+    if (T <= kPlanSmallT) {
+        plan_small_kernel<<<1, kPlanThreads, 0, st>>>(src, T, E, cap, K, counts, offsets, row_src, row_expert, row_w, tok_rows,
+                                                      status);
+        HDMOE_CHECK_LAUNCH();
+        return HDMOE_OK;
+    }
+    const int G = plan_groups_per_tile(T);
+    const int ngroups = (T + kPlanThreads - 1) / kPlanThreads;
+    const int ntiles = (ngroups + G - 1) / G;
     int32_t* tilecnt = (int32_t*)workspace;
     int32_t* tileoff = tilecnt + (size_t)E * ntiles;
-    plan_count_kernel<<<ntiles, kPlanThreads, 0, st>>>(sparse_w, T, E, ntiles, tilecnt);
+    plan_count_kernel<<<ntiles, kPlanThreads, 0, st>>>(src, T, E, ntiles, G, tilecnt);
     HDMOE_CHECK_LAUNCH();
     plan_scan_kernel<<<1, 1024, 0, st>>>(tilecnt, E, ntiles, cap, tileoff, counts, offsets, status);
     HDMOE_CHECK_LAUNCH();
-    plan_scatter_kernel<<<ntiles, kPlanThreads, 0, st>>>(sparse_w, T, E, ntiles, cap, K, tileoff, row_src, row_expert,
-                                                         row_w, tok_rows, status);
+    plan_scatter_kernel<<<ntiles, kPlanThreads, 0, st>>>(src, T, E, ntiles, G, cap, K, tileoff, row_src, row_expert, row_w,
+                                                         tok_rows, status);
     HDMOE_CHECK_LAUNCH();
     plan_tail_kernel<<<grid_for(cap, 256, 2), 256, 0, st>>>(offsets, E, cap, row_src, row_expert, row_w);
     HDMOE_CHECK_LAUNCH();
     return HDMOE_OK;
+}
+
+extern "C" int hdmoe_dispatch_plan(const float* sparse_w, int T, int E, int cap, int K, int32_t* counts,
+                                   int32_t* offsets, int32_t* row_src, int32_t* row_expert, float* row_w,
+                                   int32_t* tok_rows, int32_t* status, void* workspace, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(sparse_w, "dispatch_plan: null pointer");
+    PlanSrc src{sparse_w, nullptr, nullptr, 0};
+    return dispatch_plan_impl(src, T, E, cap, K, counts, offsets, row_src, row_expert, row_w, tok_rows, status, workspace,
+                              stream);
+}
+
+extern "C" int hdmoe_dispatch_plan_topk(const int32_t* topk_idx, const float* topk_w, int T, int E, int K, int cap,
+                                        int32_t* counts, int32_t* offsets, int32_t* row_src, int32_t* row_expert,
+                                        float* row_w, int32_t* tok_rows, int32_t* status, void* workspace,
+                                        hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(topk_idx && topk_w, "dispatch_plan_topk: null pointer");
+    HDMOE_CHECK_ARG(K >= 1 && K <= HDMOE_MAX_TOPK, "dispatch_plan_topk: 1 <= K <= %d", HDMOE_MAX_TOPK);
+    PlanSrc src{nullptr, topk_idx, topk_w, K};
+    return dispatch_plan_impl(src, T, E, cap, K, counts, offsets, row_src, row_expert, row_w, tok_rows, status, workspace,
+                              stream);
 }
 
 extern "C" int hdmoe_permute_rows(const void* const* srcs, void* const* dsts, const int64_t* row_bytes, int n_tensors,

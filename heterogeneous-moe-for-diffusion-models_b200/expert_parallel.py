@@ -6,15 +6,15 @@ after (combine).  The reference has no distributed code at all; t
 same global batch is the parity target.
 
 Per layer:
-  1. the local dispatch plan is built on the router output with the expert columns reordered by owner rank,
-     so the permuted rows are already destination-major: the gather kernel writes the all-to-all send buffer
-     directly (image | time | text packed per row);
-  2. per-expert counts are all-gathered (G x E int32) -> send / receive split sizes;
-  3. all-to-all-v of the packed rows;
-  4. received rows are regrouped expert-major with a second (one-hot) dispatch plan, the local experts run
-     (grouped tcgen05 path when available), the rows are put back in arrival order;
-  5. all-to-all-v back; gate-weighted combine with the local plan, ascending expert order (the weights are
-     applied at the token's home rank in fp32, preserving the reference's summation order).
+  1. the local dispatch plan is built on the router output with the expert columns reordered by owner rank and
+     spread into one fixed-size segment per destination rank: the gather kernel writes the all-to-all send buffers
+     (image, time, text rows) directly;
+  2. per-expert counts are all-gathered (G x E) and stay on the device;
+  3. equal-split all-to-alls of the row buffers (static sizes: the layer is CUDA-graph capturable);
+  4. received rows are compacted expert-major with one index gather computed from the counts on the device, the local
+     experts run (grouped tcgen05 path when available), outputs return to their arrival slots with one index copy;
+  5. all-to-all back; gate-weighted combine with the local plan, ascending expert order (the weights are applied at
+     the token's home rank in fp32, preserving the reference's summation order).
 
 Placement balances COST, not count: a 5x5 U-Net expert costs 2.7x a 3x3 one.
 """
@@ -68,24 +68,28 @@ def split_sizes(counts_all: torch.Tensor, placement: ExpertPlacement, order: Lis
 
 
 # ------------------------------------------------------------------------------------------------- all-to-all
-class _AllToAllV(torch.autograd.Function):
+class _AllToAllEq(torch.autograd.Function):
+    """Equal-split all-to-all of [G * C, D] buffers (segment g of the input goes to rank g; segment s of the output came
+    from rank s).  Fixed sizes: no host-side split computation, so the call is CUDA-graph capturable; its own backward."""
+
     @staticmethod
-    def forward(ctx, x, send, recv, group):
-        ctx.send, ctx.recv, ctx.group = send, recv, group
-        out = x.new_empty((sum(recv),) + tuple(x.shape[1:]))
-        dist.all_to_all_single(out, x.contiguous(), output_split_sizes=recv, input_split_sizes=send, group=group)
+    def forward(ctx, x, group):
+        ctx.group = group
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        dist.all_to_all_single(out, x, group=group)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        out = g.new_empty((sum(ctx.send),) + tuple(g.shape[1:]))
-        dist.all_to_all_single(out, g.contiguous(), output_split_sizes=ctx.send, input_split_sizes=ctx.recv,
-                               group=ctx.group)
-        return out, None, None, None
+        g = g.contiguous()
+        out = torch.empty_like(g)
+        dist.all_to_all_single(out, g, group=ctx.group)
+        return out, None
 
 
-def all_to_all_rows(x, send, recv, group=None):
-    return _AllToAllV.apply(x, list(send), list(recv), group)
+def all_to_all_equal(x, group=None):
+    return _AllToAllEq.apply(x, group)
 
 
 # ------------------------------------------------------------------------------------------------- the layer
@@ -103,62 +107,149 @@ class LocalOps:
                         combine=lambda rows, w, plan, out_dtype: ops.combine(rows, w, plan, out_dtype=out_dtype))
 
 
+@dataclass
+class LocalRows:
+    """What the local experts see: rows grouped expert-major (`row_expert`, -1 = unused), live count on the device."""
+    cap: int
+    E: int
+    counts: torch.Tensor
+    offsets: torch.Tensor
+    row_expert: torch.Tensor
+    n_rows_dev: torch.Tensor
+    status: torch.Tensor
+    _host: Optional[List[int]] = None
+
+    def host_offsets(self) -> List[int]:          # per-expert fallback paths only (synchronises)
+        if self._host is None:
+            self._host = self.offsets.tolist()
+        return self._host
+
+
+_CONST = {}
+
+# overflow flags of the fixed-capacity exchange (one 0-dim int tensor per layer call; checked lazily by check_overflow)
+_OVERFLOW: List[torch.Tensor] = []
+
+
+def check_overflow() -> None:
+    """Raise if any expert-parallel layer since the last call received more rows than its capacity (synchronises)."""
+    if _OVERFLOW:
+        bad = int(torch.stack(_OVERFLOW).max())
+        _OVERFLOW.clear()
+        if bad:
+            raise RuntimeError("hdmoe_b200 expert parallelism: a rank received more rows than capacity_factor allows; "
+                               "raise capacity_factor (None = exact worst case)")
+
+
 def ep_moe_layer(x: torch.Tensor, out_router: torch.Tensor, time_emb: torch.Tensor, text_emb: Optional[torch.Tensor],
                  run_local_experts: Callable, placement: ExpertPlacement, top_k: int, group=None,
-                 local_ops: Optional[LocalOps] = None, payload_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """Expert-parallel `router_to_unet_experts` (models/model_config2.py:11-39 semantics on the global batch).
+                 local_ops: Optional[LocalOps] = None, payload_dtype: Optional[torch.dtype] = None,
+                 capacity_factor: Optional[float] = None) -> torch.Tensor:
+    """Expert-parallel `router_to_unet_experts` (models/model_config2.py:11-39 semantics on the global batch) with
+    STATIC shapes: no host read of split sizes, so the whole layer (and the train step around it) records into a
+    CUDA graph.
 
-    run_local_experts(local_ids, plan, x_rows, time_rows, text_rows) -> out rows [plan.cap, C, H, W]: runs this
-    rank's experts (local_ids, in placement order) on rows grouped expert-major by `plan`."""
+    Layout.  C = T * k rows is what one rank can send to one peer in the worst case.  The local (destination-major)
+    dispatch plan is spread into G segments of C slots (holes carry row_src = -1 and are zero-filled by the gather
+    kernel), so ONE gather writes the all-to-all send buffers of the image / time / text rows directly (no packing
+    copy); equal-split all-to-alls move them; the G x E per-expert counts (one all-gather of E int64) tell every rank,
+    on the device, where its experts' rows sit in the received segments.  The received rows are compacted expert-major
+    with one index gather (capacity `capacity_factor * C` rows, default G * C = exact worst case; an overflow sets a
+    flag that `check_overflow()` raises on), the local experts run with device-side counts, the outputs return to their
+    arrival slots with one index copy, travel back, and the gate-weighted combine runs at the token's home rank in
+    ascending expert order (fp32, the reference's summation order).
+
+    run_local_experts(local_ids, rows: LocalRows, x_rows, time_rows, text_rows) -> out rows [rows.cap, C, H, W]."""
+    from .ops import DispatchPlan
     lo = local_ops or LocalOps.cuda()
     rank = dist.get_rank(group)
     G = placement.world
     order = placement.order()
+    E = len(order)
+    dev = x.device
     if text_emb is not None and text_emb.ndim == 3:
         text_emb = text_emb.mean(dim=1)
     dt = payload_dtype or x.dtype
     T = x.shape[0]
     img_shape = tuple(x.shape[1:])
     n_img = x[0].numel()
-    # 1. destination-major local plan
-    w_perm = out_router[:, order]
+    i64 = dict(dtype=torch.int64, device=dev)
+    # 1. destination-major local plan, spread into G segments of C slots
+    ck = (tuple(placement.owner), str(dev), rank)
+    if ck not in _CONST:      # host -> device constants are created once, outside any stream capture (warm-up iterations)
+        _CONST[ck] = (torch.tensor([placement.owner[e] for e in order], **i64), torch.tensor(order, **i64),
+                      torch.tensor([j for j, e in enumerate(order) if placement.owner[e] == rank], **i64))
+    owner_col, order_t, mine_t = _CONST[ck]
+    w_perm = out_router.index_select(1, order_t)
     plan = lo.plan(w_perm, top_k)
-    packed = torch.cat([x.reshape(T, -1).to(dt), time_emb.to(dt)] + ([text_emb.to(dt)] if text_emb is not None else []),
-                       dim=1)
-    (rows,) = lo.permute(plan, packed)
-    # 2. counts -> splits (one G x E int32 all-gather + one host read)
-    counts = plan.counts.to(torch.int64)
-    gathered = [torch.empty_like(counts) for _ in range(G)]
-    dist.all_gather(gathered, counts, group=group)
-    counts_all = torch.stack(gathered).cpu()
-    send, recv, recv_counts = split_sizes(counts_all, placement, order, rank)
-    R = sum(send)
-    # 3. dispatch all-to-all
-    got = all_to_all_rows(rows[:R], send, recv, group)
-    # 4. regroup expert-major on this rank, run the local experts, restore arrival order
+    C = plan.cap
+    cnt = plan.counts.to(torch.int64)
+    send_cnt = torch.zeros(G, **i64).index_add_(0, owner_col, cnt)
+    send_end = torch.cumsum(send_cnt, 0)
+    send_off = send_end - send_cnt
+    r = torch.arange(C, **i64)
+    dest = torch.searchsorted(send_end, r, right=True).clamp_(max=G - 1)
+    slot = torch.where(r < send_end[-1], dest * C + (r - send_off[dest]), torch.full_like(r, G * C))    # G*C = dump slot
+
+    def spread(v, fill):
+        out = torch.full((G * C + 1,), fill, dtype=v.dtype, device=dev).scatter_(0, slot, v)
+        out[G * C] = fill
+        return out[:G * C]
+
+    tok_rows = plan.tok_rows.to(torch.int64)
+    tok_rows_s = torch.where(tok_rows >= 0, slot[tok_rows.clamp(min=0)], tok_rows).to(torch.int32)
+    offsets_s = plan.offsets.clone()
+    offsets_s[E] = G * C                                     # every slot is visited; holes are zero-filled
+    splan = DispatchPlan(T, E, plan.K, G * C, plan.counts, offsets_s, spread(plan.row_src, -1),
+                         spread(plan.row_expert, -1), spread(plan.row_w, 0.0), tok_rows_s, plan.status)
+    srcs = [x.reshape(T, -1).to(dt), time_emb.to(dt)] + ([text_emb.to(dt)] if text_emb is not None else [])
+    send = lo.permute(splan, *srcs)                          # each [G * C, D_i]: the all-to-all send buffers
+    # 2. per-expert counts of every rank (device)
+    counts_flat = torch.empty(G * E, **i64)
+    dist.all_gather_into_tensor(counts_flat, cnt.contiguous(), group=group)
+    counts_all = counts_flat.view(G, E)
+    # 3. dispatch all-to-alls (equal splits)
+    got = [all_to_all_equal(s_, group) for s_ in send]
+    # 4. compact this rank's rows expert-major
     local_ids = placement.local(rank)
-    n_loc = max(len(local_ids), 1)
-    flat = [c for rc in recv_counts for c in rc]
-    ids = torch.arange(len(local_ids), device=x.device).repeat(G) if local_ids else torch.zeros(0, dtype=torch.long,
-                                                                                             device=x.device)
-    row_e = torch.repeat_interleave(ids, torch.tensor(flat, device=x.device, dtype=torch.long)) if flat else ids
-    Rr = got.shape[0]
-    if Rr > 0:
-        onehot = torch.zeros(Rr, n_loc, dtype=torch.float32, device=x.device)
-        onehot[torch.arange(Rr, device=x.device), row_e] = 1.0
-        lplan = lo.plan(onehot, 1)
-        (grows,) = lo.permute(lplan, got)
-        xr = grows[:, :n_img].reshape((-1,) + img_shape)
-        tr = grows[:, n_img:n_img + time_emb.shape[1]]
-        txr = grows[:, n_img + time_emb.shape[1]:] if text_emb is not None else None
-        out_rows = run_local_experts(local_ids, lplan, xr, tr, txr)
-        back = lo.combine(out_rows.reshape(out_rows.shape[0], -1).to(dt).contiguous(), onehot, lplan, dt)
+    mine = [j for j, e in enumerate(order) if placement.owner[e] == rank]
+    n_loc = max(len(mine), 1)
+    capR = G * C if capacity_factor is None else min(G * C, int(capacity_factor * C + 0.5))
+    if mine:
+        n_se = counts_all.index_select(1, mine_t)            # [G, n_loc] rows from rank s for my l-th expert
     else:
-        back = got[:, :n_img]
-    # 5. combine all-to-all and gate-weighted sum at the home rank
-    home = all_to_all_rows(back, recv, send, group)
-    pad = plan.cap - R
-    if pad > 0:
-        home = torch.cat([home, home.new_zeros(pad, home.shape[1])], dim=0)
-    out = lo.combine(home.reshape((plan.cap,) + img_shape).contiguous(), w_perm, plan, x.dtype)
-    return out
+        n_se = torch.zeros(G, 1, **i64)
+    src_prefix = torch.cumsum(n_se, 1) - n_se                # where they start inside segment s
+    seg_sizes = n_se.t().reshape(-1)                         # (expert-major, source-ascending)
+    seg_end = torch.cumsum(seg_sizes, 0)
+    seg_off = seg_end - seg_sizes
+    total = seg_end[-1]
+    j = torch.arange(capR, **i64)
+    seg = torch.searchsorted(seg_end, j, right=True).clamp_(max=n_loc * G - 1)
+    le = torch.div(seg, G, rounding_mode="floor")
+    sr = seg - le * G
+    live = j < total
+    src_index = torch.where(live, sr * C + src_prefix[sr, le] + (j - seg_off[seg]), torch.zeros_like(j))
+    if len(_OVERFLOW) >= 64:
+        _OVERFLOW[:] = [torch.stack(_OVERFLOW).max()]
+    _OVERFLOW.append((total > capR).to(torch.int32))
+    grows = [g_.index_select(0, src_index) for g_ in got]
+    cnt_loc = n_se.sum(0)
+    rows = LocalRows(cap=capR, E=n_loc, counts=cnt_loc.to(torch.int32),
+                     offsets=torch.cat([torch.zeros(1, **i64), torch.cumsum(cnt_loc, 0)]).to(torch.int32),
+                     row_expert=torch.where(live, le, torch.full_like(le, -1)).to(torch.int32),
+                     n_rows_dev=total.clamp(max=capR).to(torch.int32).reshape(1),
+                     status=torch.zeros(1, dtype=torch.int32, device=dev))
+    xr = grows[0].reshape((capR,) + img_shape)
+    tr = grows[1]
+    txr = grows[2] if text_emb is not None else None
+    if local_ids:
+        out_rows = run_local_experts(local_ids, rows, xr, tr, txr)
+        out_flat = out_rows.reshape(capR, -1).to(dt)
+    else:
+        out_flat = grows[0] * 0
+    # 5. back to the arrival slots, home, gate-weighted combine
+    back_idx = torch.where(live, src_index, torch.full_like(src_index, G * C))
+    back = out_flat.new_zeros(G * C + 1, n_img).index_copy(0, back_idx, out_flat)[:G * C]
+    home = all_to_all_equal(back, group)
+    return lo.combine(home.reshape((G * C,) + img_shape), w_perm, splan, x.dtype)

@@ -175,6 +175,30 @@ def dispatch_plan(sparse_w: torch.Tensor, top_k: Optional[int] = None) -> Dispat
     return DispatchPlan(T, E, K, cap, counts, offsets, row_src, row_expert, row_w, tok_rows, status)
 
 
+def dispatch_plan_from_topk(topk_idx: torch.Tensor, topk_w: torch.Tensor, num_experts: int) -> DispatchPlan:
+    """The same plan built from the router kernel's top-k output (router_gate's topk_idx int32 [T, K], topk_w [T, K])
+    instead of the dense [T, E] sparse-weight matrix: identical result (same criterion, weight > 0, on the same
+    values), T*K*8 bytes read."""
+    _cuda(topk_idx, topk_w)
+    lib = L.lib()
+    idx = topk_idx.detach().to(torch.int32).contiguous()
+    tw = _f32c(topk_w.detach())
+    T, K = idx.shape
+    E = int(num_experts)
+    cap = T * K
+    dev = idx.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    counts, offsets = torch.empty(E, **i32), torch.empty(E + 1, **i32)
+    row_src, row_expert = torch.empty(cap, **i32), torch.empty(cap, **i32)
+    row_w = torch.empty(cap, dtype=torch.float32, device=dev)
+    tok_rows = torch.empty(T, K, **i32)
+    status = torch.empty(1, **i32)
+    ws = torch.empty(lib.hdmoe_dispatch_plan_workspace_bytes(T, E), dtype=torch.uint8, device=dev)
+    L.check(lib.hdmoe_dispatch_plan_topk(_p(idx), _p(tw), T, E, K, cap, _p(counts), _p(offsets), _p(row_src), _p(row_expert),
+                                         _p(row_w), _p(tok_rows), _p(status), _p(ws), _st()), "dispatch_plan_topk")
+    return DispatchPlan(T, E, K, cap, counts, offsets, row_src, row_expert, row_w, tok_rows, status)
+
+
 def _permute_raw(srcs: Sequence[torch.Tensor], plan: DispatchPlan) -> List[torch.Tensor]:
     lib = L.lib()
     outs, n = [], len(srcs)

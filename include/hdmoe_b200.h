@@ -89,6 +89,12 @@ size_t hdmoe_dispatch_plan_workspace_bytes(int T, int E);
 int hdmoe_dispatch_plan(const float* sparse_w, int T, int E, int cap, int K, int32_t* counts, int32_t* offsets,
                         int32_t* row_src, int32_t* row_expert, float* row_w, int32_t* tok_rows,
                         int32_t* status, void* workspace, hdmoe_stream_t stream);
+/* Same plan from the router kernel's own top-k output (hdmoe_router_gate_fwd: topk_idx int32 [T, K], topk_w fp32
+ * [T, K]; entry (t, j) is dispatched to expert topk_idx[t, j] iff topk_w[t, j] > 0 -- the same criterion on the same
+ * values as sparse_w > 0, so the plan is bit-identical) without reading the dense [T, E] matrix: T*K*8 bytes in. */
+int hdmoe_dispatch_plan_topk(const int32_t* topk_idx, const float* topk_w, int T, int E, int K, int cap, int32_t* counts,
+                             int32_t* offsets, int32_t* row_src, int32_t* row_expert, float* row_w, int32_t* tok_rows,
+                             int32_t* status, void* workspace, hdmoe_stream_t stream);
 
 /* Gather rows: for up to 4 tensors at once, dst_i[r, :] = src_i[row_src[r], :] for r < *n_rows_dev
  * (rows r in [*n_rows_dev, cap) are zero-filled).  Rows are raw bytes (row_bytes[i] % 16 == 0 and

@@ -44,18 +44,32 @@ def _cpu_plan(sparse_w, top_k):
 
 
 def _cpu_permute(plan, *srcs):
-    R = int(plan.offsets[-1])
+    """gather stand-in: slot i takes row row_src[i]; holes (row_src < 0, the spread expert-parallel layout) and the
+    unused tail are zero"""
+    n = int(plan.offsets[plan.E])
+    live = torch.zeros(plan.cap, dtype=torch.bool)
+    live[:n] = plan.row_src[:n] >= 0
+    idx = plan.row_src.long().clamp(min=0)
     outs = []
     for s in srcs:
-        o = s.new_zeros((plan.cap,) + tuple(s.shape[1:]))
-        o[:R] = s[plan.row_src[:R].long()]
-        outs.append(o)
+        g = s[idx]
+        outs.append(torch.where(live.view((-1,) + (1,) * (s.ndim - 1)), g, torch.zeros((), dtype=s.dtype)))
     return tuple(outs)
 
 
 def _cpu_combine(rows, w, plan, out_dtype):
-    R = int(plan.offsets[-1])
-    return O.combine_rows(rows[:R], w, plan.row_src[:R].numpy(), plan.row_expert[:R].numpy(), plan.T).to(out_dtype)
+    """out[t] = sum over the token's rows (tok_rows: ascending expert) of w[t, expert] * rows[row], mul-then-add"""
+    out = torch.zeros((plan.T,) + tuple(rows.shape[1:]), dtype=rows.dtype)
+    tok = plan.tok_rows.long()
+    for j in range(tok.shape[1]):
+        r = tok[:, j]
+        ok = r >= 0
+        rc = r.clamp(min=0)
+        e = plan.row_expert.long()[rc].clamp(min=0)
+        wt = w[torch.arange(plan.T), e]
+        term = rows[rc] * wt.view((-1,) + (1,) * (rows.ndim - 1)).to(rows.dtype)
+        out = out + torch.where(ok.view((-1,) + (1,) * (rows.ndim - 1)), term, torch.zeros((), dtype=rows.dtype))
+    return out.to(out_dtype)
 
 
 CPU_OPS = EP.LocalOps(plan=_cpu_plan, permute=_cpu_permute, combine=_cpu_combine)
@@ -130,3 +144,50 @@ def test_placement_balances_cost_not_count():
     send, recv, rc = EP.split_sizes(counts_all, p, order, 0)
     mine = [j for j, e in enumerate(order) if p.owner[e] == 0]
     assert sum(send) == 10 and recv == [sum(counts_all[s][j].item() for j in mine) for s in range(2)]
+
+
+def _worker_capacity(rank, world, port, ret):
+    """capacity_factor below the worst case: exact result while the rows fit, overflow flag raised otherwise"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gen = torch.Generator().manual_seed(7 + rank)
+        T, E, k = 9, 4, 1
+        x = torch.randn(T, 2, 2, 2, generator=gen)
+        te, txt = torch.randn(T, 3, generator=gen), torch.randn(T, 2, 4, generator=gen)
+        placement = EP.ExpertPlacement([0, 0, 1, 1], world)
+
+        def run_local(local_ids, plan, xr, tr, txr):
+            off = plan.offsets.tolist()
+            outs = [_expert(e, xr[off[j]:off[j + 1]], tr[off[j]:off[j + 1]], txr[off[j]:off[j + 1]])
+                    for j, e in enumerate(local_ids)]
+            n = min(off[-1], plan.cap)
+            return torch.cat(outs + [xr.new_zeros((max(plan.cap - off[-1], 0),) + tuple(xr.shape[1:]))])[:plan.cap]
+
+        res = []
+        for skew in (False, True):
+            lg = torch.randn(T, E, generator=gen)
+            if skew:
+                lg[:, 0] += 100.0                     # every token of every rank goes to expert 0 (rank 0): 2*T rows > 1.5*T
+            sp, _, _, _ = O.router_gate_from_logits(lg, k)
+            out = EP.ep_moe_layer(x, sp, te, txt, run_local, placement, k, local_ops=CPU_OPS, capacity_factor=1.5)
+            ref = O.moe_layer(x, sp, te, txt, _expert)
+            try:
+                EP.check_overflow()
+                flagged = False
+            except RuntimeError:
+                flagged = True
+            res.append((bool(torch.allclose(out, ref, atol=1e-6)), flagged))
+        ret[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_expert_parallel_capacity_factor_and_overflow_flag():
+    world, port = 2, _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_capacity, args=(world, port, ret), nprocs=world, join=True)
+    r = dict(ret)
+    assert r[0][0] == (True, False) and r[1][0] == (True, False)        # balanced routing fits: exact, no flag
+    assert r[0][1][1] is True                                           # rank 0 overflowed and said so
+    assert r[1][1] == (False, False) or r[1][1][1] is False             # rank 1 received nothing: no flag of its own

@@ -172,6 +172,20 @@ def test_dispatch_plan_bit_exact(T, E, k, mf):
         inv[src[r], fill[src[r]]] = r
         fill[src[r]] += 1
     assert np.array_equal(tok, inv)
+    # the same plan from the router kernel's top-k pairs (T*k*8 bytes in instead of two dense passes): bit-identical
+    gen = torch.Generator().manual_seed(17 + T)
+    lg = torch.randn(T, E, generator=gen)
+    if mf:
+        lg = lg.masked_fill(torch.rand(T, E, generator=gen) < mf, float("-inf"))
+    sp2, _, _, idx = O.router_gate_from_logits(lg, k)
+    assert torch.equal(torch.nan_to_num(sp2, nan=-1.0), torch.nan_to_num(sp, nan=-1.0))
+    tw = torch.gather(sp2, 1, idx)                     # weight of every chosen expert (0 for a -inf pick, NaN if all masked)
+    plan2 = ops.dispatch_plan_from_topk(idx.to(torch.int32).cuda(), tw.cuda(), E)
+    assert plan2.host_offsets() == off
+    for a_, b_ in ((plan2.row_src, plan.row_src), (plan2.row_expert, plan.row_expert), (plan2.tok_rows, plan.tok_rows),
+                   (plan2.counts, plan.counts)):
+        assert torch.equal(a_, b_)
+    assert torch.equal(plan2.row_w[:R], plan.row_w[:R])
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
