@@ -281,19 +281,15 @@ EP_CAPACITY = 2.0      # rows a rank's experts may receive, in units of T*k (Non
 
 
 def make_runner(args, variant, res, B, rank, world, device, parallelism, pinned=False):
-    """TrainRunner with graph capture; expert-parallel capture failures fall back to the eager step (reported)."""
-    try:
-        return TrainRunner(variant, res, B, rank, world, device, parallelism, use_graph=not args.no_graph,
-                           warmup=args.warmup, pinned=pinned)
-    except Exception:                                # noqa: BLE001
-        import traceback
-        traceback.print_exc()
-        if parallelism != "ep":
-            raise
-        sys.stderr.write("bench.py: graph capture of the expert-parallel step failed, using the eager step\n")
-        r = TrainRunner(variant, res, B, rank, world, device, parallelism, use_graph=False, warmup=args.warmup, pinned=pinned)
-        r.note = "eager (graph capture of the expert-parallel step failed)"
-        return r
+    """TrainRunner; data-parallel steps are recorded as CUDA graphs.  The expert-parallel step has static shapes and no
+    host synchronisation (it records), but replaying NCCL all-to-alls from inside the graph deadlocked on this
+    torch 2.11 / NCCL 2.28 stack (2 x B200, round-2 log), so it runs eagerly unless --ep-graph is given."""
+    ep = parallelism == "ep" and world > 1
+    use_graph = (not args.no_graph) and (not ep or args.ep_graph)
+    r = TrainRunner(variant, res, B, rank, world, device, parallelism, use_graph=use_graph, warmup=args.warmup, pinned=pinned)
+    if ep and not use_graph:
+        r.note = "eager (static-shape expert-parallel step; NCCL-in-graph replay disabled)"
+    return r
 
 
 def run_ours(args):
@@ -860,6 +856,7 @@ def main():
     ap.add_argument("--no-sampler", action="store_true", help="skip the EDM sampler throughput extra")
     ap.add_argument("--parallelism", default="dp", choices=["dp", "ep"], help="N>1: data-parallel replicas or expert-parallel U-Net experts")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the whole-step CUDA graph")
+    ap.add_argument("--ep-graph", action="store_true", help="record the expert-parallel step (NCCL all-to-alls inside the graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -193,13 +193,13 @@ def ep_moe_layer(x: torch.Tensor, out_router: torch.Tensor, time_emb: torch.Tens
 
     def spread(v, fill):
         out = torch.full((G * C + 1,), fill, dtype=v.dtype, device=dev).scatter_(0, slot, v)
-        out[G * C] = fill
+        out[G * C:].fill_(fill)          # (fill_ is a kernel; indexed scalar assignment would copy from the host)
         return out[:G * C]
 
     tok_rows = plan.tok_rows.to(torch.int64)
     tok_rows_s = torch.where(tok_rows >= 0, slot[tok_rows.clamp(min=0)], tok_rows).to(torch.int32)
     offsets_s = plan.offsets.clone()
-    offsets_s[E] = G * C                                     # every slot is visited; holes are zero-filled
+    offsets_s[E:E + 1].fill_(G * C)                          # every slot is visited; holes are zero-filled
     splan = DispatchPlan(T, E, plan.K, G * C, plan.counts, offsets_s, spread(plan.row_src, -1),
                          spread(plan.row_expert, -1), spread(plan.row_w, 0.0), tok_rows_s, plan.status)
     srcs = [x.reshape(T, -1).to(dt), time_emb.to(dt)] + ([text_emb.to(dt)] if text_emb is not None else [])
