@@ -343,23 +343,30 @@ class HDMOEM(nn.Module):
         te = self.out_fourier1(self.Fourier_emb(time_vec))
         te = self.out_fourier2(util.mp_silu(te))
         feats = self.input_proj(x)
+        glue = _FUSED_GLUE[0] and x.is_cuda and x.dtype == torch.float32 and self.internal_channels == 32
         if self._variant == 2:      # models/model_config2.py:244-249
-            vw = torch.sigmoid((time_vec * 4 - transition_point) / softness).view(-1, 1, 1, 1)
-            s_vit = (vw + 1e-2) * 2
-            s_unet = ((1.0 - vw) + 1e-2) * 2
-            scaling = torch.cat([s_vit, s_unet], dim=1).view(-1, 2)
+            if glue:
+                scaling = ops.analytic_scaling(time_vec, transition_point, softness)      # one launch, [B, 2]
+            else:
+                vw = torch.sigmoid((time_vec * 4 - transition_point) / softness).view(-1, 1, 1, 1)
+                scaling = torch.cat([(vw + 1e-2) * 2, ((1.0 - vw) + 1e-2) * 2], dim=1).view(-1, 2)
         else:                       # models/model_config1.py:246-249
             scaling = self.scaling_net(x=te, zeta=zeta, noise=noise.get("scaling"))
-            s_vit = scaling[:, 0:1].view(-1, 1, 1, 1)
-            s_unet = scaling[:, 1:2].view(-1, 1, 1, 1)
-        in_unet = s_unet * feats
-        in_vit = s_vit * feats
+        s_vit = scaling[:, 0:1].view(-1, 1, 1, 1)
+        s_unet = scaling[:, 1:2].view(-1, 1, 1, 1)
         # router trunks of both routers as grouped tcgen05 launches (bf16 configuration): pooled features up front
         trunk = self._router_trunk(x)
         pool_vit = pool_un = None
-        if trunk is not None:
-            pool_vit, pool_un = trunk([in_vit, in_unet], self.training)
-        glue = _FUSED_GLUE[0] and x.is_cuda and x.dtype == torch.float32 and self.internal_channels == 32
+        if glue:
+            # one pass over feats: both scaled branch inputs and the channels-last bf16 router-trunk input
+            in_vit, in_unet, trunk_in = ops.scale_pair(feats, scaling, want_trunk=trunk is not None)
+            if trunk is not None:
+                pool_vit, pool_un = trunk(None, self.training, pre_nhwc=trunk_in)
+        else:
+            in_unet = s_unet * feats
+            in_vit = s_vit * feats
+            if trunk is not None:
+                pool_vit, pool_un = trunk([in_vit, in_unet], self.training)
         # the ViT router is evaluated first (RNG order, quirk Q2)
         if _BRANCH_STREAMS[0] and x.is_cuda and _EP["placement"] is None:
             # ViT branch (router + MoE layer) beside the U-Net branch; host program order as in the reference

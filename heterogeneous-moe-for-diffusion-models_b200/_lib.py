@@ -86,6 +86,12 @@ PROTOTYPES = {
     "hdmoe_trunk_swap_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _p]),
     "hdmoe_trunk_gate_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _f, _f, _p]),
     "hdmoe_trunk_gate_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _f, _f, _p]),
+    "hdmoe_analytic_scaling": (_i, [_p, _f, _f, _p, _i, _p]),
+    "hdmoe_scale_pair_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i64, _p]),
+    "hdmoe_scale_pair_tiles": (_i, [_i64]),
+    "hdmoe_scale_pair_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i64, _p]),
+    "hdmoe_sqerr_rows": (_i, [_p, _p, _p, _i, _i64, _p]),
+    "hdmoe_sqerr_rows_bwd": (_i, [_p, _p, _p, _p, _i, _i64, _p]),
     "hdmoe_optim_chunk_elems": (_i, []),
     "hdmoe_adamw_step": (_i, [_p, _i, _i, _p, _p, _p, _f, _f, _f, _f, _i, _p]),
 }

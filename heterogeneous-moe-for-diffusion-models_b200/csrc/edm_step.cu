@@ -290,3 +290,59 @@ extern "C" int hdmoe_edm_heun_correct(const float* x_hat, const float* x_next, c
     HDMOE_CHECK_LAUNCH();
     return HDMOE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// EDM_LOSS data term (Utils/utils.py:135-146): every loss term that touches the images depends on them only through the
+// per-sample squared error se[b] = sum_i (D[b,i] - x0[b,i])^2 (log_var is one scalar per sample), so the activation-
+// sized part of the loss is ONE reduction kernel forward and ONE scaling kernel backward; the remaining arithmetic runs
+// on [B]-sized vectors.  One CTA per sample, fixed summation order (deterministic).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace hdmoe {
+__global__ void __launch_bounds__(256)
+sqerr_rows_kernel(const float4* __restrict__ d, const float4* __restrict__ x, float* __restrict__ se, long long per4) {
+    __shared__ float red[8];
+    const float4* dr = d + (size_t)blockIdx.x * per4;
+    const float4* xr = x + (size_t)blockIdx.x * per4;
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < per4; i += 256) {
+        const float4 a = dr[i], b = xr[i];
+        const float e0 = a.x - b.x, e1 = a.y - b.y, e2 = a.z - b.z, e3 = a.w - b.w;
+        s += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        se[blockIdx.x] = t;
+    }
+}
+// dD[b, i] = 2 * (D - x0) * g[b]
+__global__ void __launch_bounds__(256)
+sqerr_rows_bwd_kernel(const float4* __restrict__ d, const float4* __restrict__ x, const float* __restrict__ g,
+                      float4* __restrict__ dd, long long per4, long long n4) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float c = 2.f * g[i / per4];
+        const float4 a = d[i], b = x[i];
+        dd[i] = make_float4(c * (a.x - b.x), c * (a.y - b.y), c * (a.z - b.z), c * (a.w - b.w));
+    }
+}
+}  // namespace hdmoe
+
+extern "C" int hdmoe_sqerr_rows(const float* d, const float* x, float* se, int B, int64_t per, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(d && x && se && B >= 1 && per >= 4 && per % 4 == 0, "sqerr_rows: bad args (row length must be a multiple of 4)");
+    hdmoe::sqerr_rows_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float4*)d, (const float4*)x, se, per / 4);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_sqerr_rows_bwd(const float* d, const float* x, const float* g_se, float* dd, int B, int64_t per,
+                                    hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(d && x && g_se && dd && B >= 1 && per >= 4 && per % 4 == 0, "sqerr_rows_bwd: bad args");
+    const long long n4 = (long long)B * per / 4;
+    hdmoe::sqerr_rows_bwd_kernel<<<hdmoe::grid_for(n4, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)d, (const float4*)x, g_se, (float4*)dd, per / 4, n4);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}

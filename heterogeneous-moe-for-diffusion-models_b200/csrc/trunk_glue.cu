@@ -319,6 +319,104 @@ static constexpr int kGateFwdSmem = (2 * kGC * kGC + 2 * kGC + kGT * (2 * kGC + 
 static constexpr int kGateBwdSmem =
     (2 * (2 * kGC * kGC) + 2 * kGC + kGT * (kGC + 1) + kGT * (2 * kGC + 1) + kGT * 2 + kGT * (kGC + 1)) * (int)sizeof(float);
 
+// ------------------------------------------------------------------------------------------------ branch scaling
+// models/model_config2.py:244-251 (analytic sigma-sigmoid path scaling) and models/model_config1.py:246-252 (learned
+// Scaling_router gains): in_vit = s_vit[b] * feats, in_unet = s_unet[b] * feats.  ONE pass over the features writes
+// both products (fp32 NCHW, the dispatch payload source) AND the channels-last bf16 copy [2B, HW, C] the tcgen05 router
+// trunk reads (rows [0, B) = ViT router input, [B, 2B) = U-Net router input) instead of 2 broadcast multiplies + 2 casts
+// + a concatenation + a layout kernel.  Tile = 32 pixels x 32 channels, transposed through shared memory.
+__global__ void __launch_bounds__(256)
+analytic_scaling_kernel(const float* __restrict__ time_vec, float tp, float soft, float* __restrict__ scaling, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float w = 1.f / (1.f + expf(-(time_vec[b] * 4.f - tp) / soft));
+    scaling[2 * b] = (w + 1e-2f) * 2.f;                  // ViT path
+    scaling[2 * b + 1] = ((1.f - w) + 1e-2f) * 2.f;      // U-Net path
+}
+
+__global__ void __launch_bounds__(256)
+scale_pair_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ scaling, float* __restrict__ in_v,
+                      float* __restrict__ in_u, __nv_bfloat16* __restrict__ trunk, int B, int HW) {
+    __shared__ float tile[kGC][33];
+    const int b = blockIdx.y, p0 = blockIdx.x * 32;
+    const float sv = scaling[2 * b], su = scaling[2 * b + 1];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;          // 8 warps: warp wq handles channels wq, wq+8, ...
+    const size_t base = (size_t)b * kGC * HW;
+#pragma unroll
+    for (int cc = 0; cc < kGC / 8; ++cc) {
+        const int c = wq + 8 * cc, p = p0 + lane;
+        float f = 0.f;
+        if (p < HW) {
+            f = feats[base + (size_t)c * HW + p];
+            in_v[base + (size_t)c * HW + p] = sv * f;
+            in_u[base + (size_t)c * HW + p] = su * f;
+        }
+        tile[c][lane] = f;
+    }
+    if (!trunk) return;
+    __syncthreads();
+    // channels-last: thread (pixel = threadIdx.x / 8, channel quad = threadIdx.x % 8) writes 4 bf16 (8 bytes)
+    const int px = threadIdx.x >> 3, cq = (threadIdx.x & 7) * 4, p = p0 + px;
+    if (p < HW) {
+        const float f0 = tile[cq][px], f1 = tile[cq + 1][px], f2 = tile[cq + 2][px], f3 = tile[cq + 3][px];
+        Vec4<__nv_bfloat16>::store(trunk + ((size_t)b * HW + p) * kGC + cq, make_float4(sv * f0, sv * f1, sv * f2, sv * f3));
+        Vec4<__nv_bfloat16>::store(trunk + ((size_t)(B + b) * HW + p) * kGC + cq, make_float4(su * f0, su * f1, su * f2, su * f3));
+    }
+}
+
+// d_feats = s_v * (g_v + g_trunk_v) + s_u * (g_u + g_trunk_u);  ds_part[b][tile][2] = sum over the tile of feats * g
+__global__ void __launch_bounds__(256)
+scale_pair_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ scaling, const float* __restrict__ g_v,
+                      const float* __restrict__ g_u, const __nv_bfloat16* __restrict__ g_trunk, float* __restrict__ d_feats,
+                      float* __restrict__ ds_part, int B, int HW) {
+    __shared__ float tv[kGC][33], tu[kGC][33];
+    __shared__ float red[2][8];
+    const int b = blockIdx.y, p0 = blockIdx.x * 32;
+    const float sv = scaling[2 * b], su = scaling[2 * b + 1];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const size_t base = (size_t)b * kGC * HW;
+    if (g_trunk) {
+        const int px = threadIdx.x >> 3, cq = (threadIdx.x & 7) * 4, p = p0 + px;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+        if (p < HW) {
+            a = Vec4<__nv_bfloat16>::load(g_trunk + ((size_t)b * HW + p) * kGC + cq);
+            c = Vec4<__nv_bfloat16>::load(g_trunk + ((size_t)(B + b) * HW + p) * kGC + cq);
+        }
+        tv[cq][px] = a.x; tv[cq + 1][px] = a.y; tv[cq + 2][px] = a.z; tv[cq + 3][px] = a.w;
+        tu[cq][px] = c.x; tu[cq + 1][px] = c.y; tu[cq + 2][px] = c.z; tu[cq + 3][px] = c.w;
+        __syncthreads();
+    }
+    float av = 0.f, au = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < kGC / 8; ++cc) {
+        const int c = wq + 8 * cc, p = p0 + lane;
+        if (p < HW) {
+            const size_t i = base + (size_t)c * HW + p;
+            float gv = g_v ? g_v[i] : 0.f, gu = g_u ? g_u[i] : 0.f;
+            if (g_trunk) {
+                gv += tv[c][lane];
+                gu += tu[c][lane];
+            }
+            const float f = feats[i];
+            d_feats[i] = sv * gv + su * gu;
+            av = fmaf(f, gv, av);
+            au = fmaf(f, gu, au);
+        }
+    }
+    av = warp_sum(av);
+    au = warp_sum(au);
+    if (lane == 0) {
+        red[0][wq] = av;
+        red[1][wq] = au;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+        ds_part[((size_t)b * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = t;
+    }
+}
+
 }  // namespace hdmoe
 using namespace hdmoe;
 
@@ -371,6 +469,39 @@ extern "C" int hdmoe_trunk_gate_bwd(const float* u, const float* a, const float*
     const int grid = (int)(nbatch < kNumSMs ? nbatch : kNumSMs);      // persistent: dW partials stay in registers
     gate_bwd_kernel<<<grid, kGT, kGateBwdSmem, (cudaStream_t)stream>>>(u, a, b, alpha_txt, W1, W2, d_mix, d_g, du, da, db, dW1, dW2,
                                                                       d_alpha, P, HW, k);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_analytic_scaling(const float* time_vec, float transition_point, float softness, float* scaling, int B,
+                                      hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(time_vec && scaling && B >= 1 && softness != 0.f, "analytic_scaling: bad args");
+    analytic_scaling_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(time_vec, transition_point, softness, scaling, B);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_scale_pair_fwd(const float* feats, const float* scaling, float* in_vit, float* in_unet, void* trunk_bf16,
+                                    int B, int C, int64_t HW, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(feats && scaling && in_vit && in_unet && B >= 1 && HW >= 1 && B <= 65535, "scale_pair_fwd: bad args");
+    HDMOE_CHECK_ARG(C == kGC, "scale_pair_fwd: internal_channels must be %d (got %d)", kGC, C);
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)B);
+    scale_pair_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feats, scaling, in_vit, in_unet, (__nv_bfloat16*)trunk_bf16, B,
+                                                                  (int)HW);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_scale_pair_tiles(int64_t HW) { return (int)((HW + 31) / 32); }
+
+extern "C" int hdmoe_scale_pair_bwd(const float* feats, const float* scaling, const float* g_vit, const float* g_unet,
+                                    const void* g_trunk_bf16, float* d_feats, float* ds_part, int B, int C, int64_t HW,
+                                    hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(feats && scaling && d_feats && ds_part && B >= 1 && HW >= 1 && B <= 65535, "scale_pair_bwd: bad args");
+    HDMOE_CHECK_ARG(C == kGC, "scale_pair_bwd: internal_channels must be %d (got %d)", kGC, C);
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)B);
+    scale_pair_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feats, scaling, g_vit, g_unet,
+                                                                  (const __nv_bfloat16*)g_trunk_bf16, d_feats, ds_part, B, (int)HW);
     HDMOE_CHECK_LAUNCH();
     return HDMOE_OK;
 }

@@ -126,6 +126,9 @@ class Router(nn.Module):
         sparse, probs, logits, idx, tw, stats = ops.router_gate(pooled, cond, w_hat, self.k, noise=noise,
                                                                 zeta=float(zeta), mask=mask)
         self.last = {"topk_idx": idx, "topk_w": tw, "stats": stats}
+        # the load-balance / z-loss partial sums travel with the probabilities so that EDM_LOSS can consume them without
+        # a change of the reference's return structure (hdmoe_b200.utils.EDM_LOSS reads the attribute)
+        probs._hdmoe_stats = stats
         return sparse, probs, logits
 
 

@@ -856,3 +856,84 @@ def trunk_gate(u, a, b, alpha_txt, w1_hat, w2_hat, H: int, W: int, cat_t: float 
     n = math.sqrt((1 - sum_t) ** 2 + sum_t ** 2)
     consts = (float(c1), float(c2), float((1 - sum_t) / n), float(sum_t / n))
     return _TrunkGate.apply(u, a, b, alpha_txt, w1_hat, w2_hat, H, W, consts)
+
+
+# ----------------------------------------------------------------------------------------------------
+# (10) EDM_LOSS data term
+# ----------------------------------------------------------------------------------------------------
+class _SqErrRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, d, x):
+        _cuda(d, x)
+        d, x = _f32c(d), _f32c(x)
+        B, per = d.shape[0], d[0].numel()
+        se = torch.empty(B, dtype=torch.float32, device=d.device)
+        L.check(L.lib().hdmoe_sqerr_rows(_p(d), _p(x), _p(se), B, per, _st()), "sqerr_rows")
+        ctx.save_for_backward(d, x)
+        return se
+
+    @staticmethod
+    def backward(ctx, g):
+        d, x = ctx.saved_tensors
+        B, per = d.shape[0], d[0].numel()
+        dd = torch.empty_like(d)
+        L.check(L.lib().hdmoe_sqerr_rows_bwd(_p(d), _p(x), _p(_f32c(g)), _p(dd), B, per, _st()), "sqerr_rows_bwd")
+        return dd, None
+
+
+def sqerr_rows(d, x0):
+    """se[b] = sum over the sample of (d - x0)^2 (fp32, deterministic); gradient flows to d only (x0 is data)."""
+    return _SqErrRows.apply(d, x0)
+
+
+# ----------------------------------------------------------------------------------------------------
+# (11) branch scaling (csrc/trunk_glue.cu)
+# ----------------------------------------------------------------------------------------------------
+def analytic_scaling(time_vec, transition_point: float, softness: float):
+    """[B, 2] = ((w + .01) * 2, (1 - w + .01) * 2), w = sigmoid((4 t - tp) / soft); models/model_config2.py:244-249.
+    time_vec is data (log sigma / 4): no gradient."""
+    _cuda(time_vec)
+    t = _f32c(time_vec.detach()).reshape(-1)
+    out = torch.empty(t.numel(), 2, dtype=torch.float32, device=t.device)
+    L.check(L.lib().hdmoe_analytic_scaling(_p(t), float(transition_point), float(softness), _p(out), t.numel(), _st()),
+            "analytic_scaling")
+    return out
+
+
+class _ScalePair(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, scaling, want_trunk):
+        _cuda(feats, scaling)
+        feats, scaling = _f32c(feats), _f32c(scaling)
+        B, Cn, H, W = feats.shape
+        assert scaling.shape == (B, 2)
+        in_v, in_u = torch.empty_like(feats), torch.empty_like(feats)
+        trunk = torch.empty(2 * B, H, W, Cn, dtype=torch.bfloat16, device=feats.device) if want_trunk else None
+        L.check(L.lib().hdmoe_scale_pair_fwd(_p(feats), _p(scaling), _p(in_v), _p(in_u), _p(trunk), B, Cn, H * W, _st()),
+                "scale_pair_fwd")
+        ctx.save_for_backward(feats, scaling)
+        ctx.want_trunk = want_trunk
+        if want_trunk:
+            return in_v, in_u, trunk
+        ctx.mark_non_differentiable()
+        return in_v, in_u, None
+
+    @staticmethod
+    def backward(ctx, g_v, g_u, g_t):
+        feats, scaling = ctx.saved_tensors
+        B, Cn, H, W = feats.shape
+        g_v = None if g_v is None else _f32c(g_v)
+        g_u = None if g_u is None else _f32c(g_u)
+        g_t = None if (g_t is None or not ctx.want_trunk) else g_t.to(torch.bfloat16).contiguous()
+        d_feats = torch.empty_like(feats)
+        tiles = L.lib().hdmoe_scale_pair_tiles(H * W)
+        part = torch.empty(B, tiles, 2, dtype=torch.float32, device=feats.device)
+        L.check(L.lib().hdmoe_scale_pair_bwd(_p(feats), _p(scaling), _p(g_v), _p(g_u), _p(g_t), _p(d_feats), _p(part), B, Cn,
+                                             H * W, _st()), "scale_pair_bwd")
+        return d_feats, part.sum(dim=1), None
+
+
+def scale_pair(feats, scaling, want_trunk: bool = False):
+    """(in_vit, in_unet, trunk_in): scaling[b, 0] * feats, scaling[b, 1] * feats (fp32 [B, C, H, W]) and optionally the
+    channels-last bf16 copy [2B, H, W, C] of both for the tcgen05 router trunk -- one pass over feats."""
+    return _ScalePair.apply(feats, scaling, want_trunk)

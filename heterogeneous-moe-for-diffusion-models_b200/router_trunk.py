@@ -187,10 +187,14 @@ class GroupedRouterTrunk:
         self._wg_pending = True
 
     # ------------------------------------------------------------------------------------------ forward
-    def __call__(self, xs, training: bool):
-        """xs: one [B, C, H, W] router input per router (any float dtype) -> list of fp32 pooled features [B, 4C]."""
+    def __call__(self, xs, training: bool, pre_nhwc=None):
+        """xs: one [B, C, H, W] router input per router (any float dtype) -> list of fp32 pooled features [B, 4C].
+        pre_nhwc: the inputs already concatenated and channels-last, bf16 [E * B, H, W, C] (ops.scale_pair writes it in
+        the same pass that scales the features); xs is ignored then."""
+        if pre_nhwc is not None:
+            xs = [pre_nhwc]
         dev = xs[0].device
-        B = xs[0].shape[0]
+        B = xs[0].shape[0] // (self.E if pre_nhwc is not None else 1)
         if self._built_for != dev:
             self._build(dev)
         key = (B, dev)
@@ -206,8 +210,11 @@ class GroupedRouterTrunk:
         else:
             self._run_prep(training)
             token = None
-        rows = torch.cat([x.to(torch.bfloat16) for x in xs], dim=0).contiguous()
-        h = nhwc.rows_to_nhwc(rows, self.layers[0].cin_pad, ones_channel=False)
+        if pre_nhwc is not None:
+            h = pre_nhwc
+        else:
+            rows = torch.cat([x.to(torch.bfloat16) for x in xs], dim=0).contiguous()
+            h = nhwc.rows_to_nhwc(rows, self.layers[0].cin_pad, ones_channel=False)
         for li, (L_, ni) in enumerate(zip(self.layers, self.NORMS)):
             if need_grad:
                 h = _GConvFn.apply(h, token, self, li)

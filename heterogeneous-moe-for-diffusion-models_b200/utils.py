@@ -33,13 +33,39 @@ class EDM_LOSS(nn.Module):
         self.Unet_lambda, self.vit_lambda, self.z_bal, self.prior_bal = Unet_bal, vit_bal, z_bal, prior_bal
 
     def forward(self, sigma_vec, x, sigma, out_model, router_stats=None):
-        err = (out_model["denoised"] - x) ** 2
+        D = out_model["denoised"]
+        E = self.num_experts
+        if router_stats is None:
+            # the fused router kernel attaches its partial sums to the tensors it returned (model_components.Router)
+            su = getattr(out_model["Unet_router_loss"], "_hdmoe_stats", None)
+            sv = getattr(out_model["vit_router_loss"], "_hdmoe_stats", None)
+            if su is not None and sv is not None:
+                router_stats = (su, sv)
+        if D.is_cuda and D.dtype == torch.float32 and x.dtype == torch.float32 and D[0].numel() % 4 == 0 and D.shape == x.shape:
+            # every image-dependent term is a function of the per-sample squared error: ONE reduction kernel forward, one
+            # scaling kernel backward (csrc/edm_step.cu), the rest on [B]-sized vectors
+            from . import ops
+            B, per = D.shape[0], D[0].numel()
+            se = ops.sqerr_rows(D, x)
+            mse = se.sum() / (B * per)
+            if out_model["log_var"] is None:
+                pure = mse
+            else:
+                lv = out_model["log_var"].clamp(min=-10, max=10).reshape(-1)
+                lv = lv.expand(B) if lv.numel() == 1 else lv
+                pure = torch.mean(se / per * torch.exp(-lv) + lv)
+            pure = pure.clamp(max=50)
+            return self._finish(pure, mse, out_model, router_stats)
+        err = (D - x) ** 2
         if out_model["log_var"] is None:
             pure = torch.mean(err)
         else:
             lv = out_model["log_var"].clamp(min=-10, max=10)
             pure = torch.mean(err / lv.exp() + lv)
         pure = pure.clamp(max=50)
+        return self._finish(pure, torch.mean(err), out_model, router_stats)
+
+    def _finish(self, pure, mse, out_model, router_stats):
         E = self.num_experts
         if router_stats is not None:
             su, sv = router_stats
@@ -53,7 +79,7 @@ class EDM_LOSS(nn.Module):
             z_u, z_v = self.z_loss(out_model["Unet_raw"]), self.z_loss(out_model["vit_raw"])
         bal = (self.Unet_lambda * lb_u + self.vit_lambda * lb_v).clamp(max=50)
         zl = (self.z_bal * z_u + self.z_bal * z_v).clamp(max=50)
-        return {"loss": (pure + zl + bal).clamp(max=50), "denoising": torch.mean(err), "balance": bal, "z_loss": zl,
+        return {"loss": (pure + zl + bal).clamp(max=50), "denoising": mse, "balance": bal, "z_loss": zl,
                 "entropy": 0.0, "pure_loss": pure}
 
     @staticmethod

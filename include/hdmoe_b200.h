@@ -353,6 +353,32 @@ int hdmoe_trunk_gate_bwd(const float* u, const float* a, const float* b, const f
                          float* dW1, float* dW2, float* d_alpha, int64_t P, int64_t HW, int C, float c1, float c2,
                          float ms_a, float ms_b, hdmoe_stream_t stream);
 
+/* Branch scaling (models/model_config2.py:244-251, models/model_config1.py:246-252).
+ *   analytic_scaling: w = sigmoid((4 * time_vec[b] - transition_point) / softness);
+ *                     scaling[b] = ((w + 0.01) * 2, (1 - w + 0.01) * 2)                 (ViT gain, U-Net gain)
+ *   scale_pair_fwd:   in_vit = scaling[b, 0] * feats, in_unet = scaling[b, 1] * feats  (fp32 [B, C, HW], C = 32) and,
+ *                     when trunk_bf16 != NULL, the channels-last bf16 copy [2B, HW, C] of both (ViT rows first) that the
+ *                     tcgen05 router trunk reads.
+ *   scale_pair_bwd:   d_feats from the gradients of the three outputs (each may be NULL); ds_part
+ *                     [B, hdmoe_scale_pair_tiles(HW), 2]: the caller sums over the tiles (deterministic) -> d scaling. */
+int hdmoe_analytic_scaling(const float* time_vec, float transition_point, float softness, float* scaling, int B,
+                           hdmoe_stream_t stream);
+int hdmoe_scale_pair_fwd(const float* feats, const float* scaling, float* in_vit, float* in_unet, void* trunk_bf16, int B,
+                         int C, int64_t HW, hdmoe_stream_t stream);
+int hdmoe_scale_pair_tiles(int64_t HW);
+int hdmoe_scale_pair_bwd(const float* feats, const float* scaling, const float* g_vit, const float* g_unet,
+                         const void* g_trunk_bf16, float* d_feats, float* ds_part, int B, int C, int64_t HW,
+                         hdmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (12) EDM_LOSS data term (Utils/utils.py:135-146): per-sample squared error se[b] = sum_i (D[b,i] - x0[b,i])^2 and its
+ *      backward dD[b,i] = 2 (D - x0) g_se[b]; every image-dependent loss term is a function of se and the per-sample
+ *      log-variance, so the rest of the loss runs on [B]-sized vectors.  fp32, row length a multiple of 4.
+ * ---------------------------------------------------------------------------------------------- */
+int hdmoe_sqerr_rows(const float* d, const float* x, float* se, int B, int64_t per, hdmoe_stream_t stream);
+int hdmoe_sqerr_rows_bwd(const float* d, const float* x, const float* g_se, float* dd, int B, int64_t per,
+                         hdmoe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

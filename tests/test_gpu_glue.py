@@ -66,3 +66,46 @@ def test_trunk_swap_matches_oracle(B, S):
     assert rel_l2(q.cpu(), q_ref) < 1e-6 and rel_l2(c.cpu(), c_ref) < 1e-6
     assert rel_l2(ud.grad.cpu(), ur.grad) < 1e-6 and rel_l2(vd.grad.cpu(), vr.grad) < 1e-6
     assert rel_l2(wd.grad.cpu(), wr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 32, 32), (2, 16, 16), (2, 20, 12)])
+@pytest.mark.parametrize("want_trunk", [False, True])
+def test_scale_pair_matches_reference_products(B, H, W, want_trunk):
+    """in_vit = s_vit * feats, in_unet = s_unet * feats (models/model_config2.py:250-251) + the channels-last bf16 copy
+    for the tcgen05 router trunk, forward and all gradients (d feats, d scaling) against float64 autograd."""
+    from hdmoe_b200 import ops
+    gen = torch.Generator().manual_seed(B + H)
+    feats = torch.randn(B, 32, H, W, generator=gen)
+    scaling = torch.rand(B, 2, generator=gen) * 2
+    gv, gu = torch.randn(B, 32, H, W, generator=gen), torch.randn(B, 32, H, W, generator=gen)
+    gt = torch.randn(2 * B, H, W, 32, generator=gen).to(torch.bfloat16)
+    fr, sr = feats.double().requires_grad_(True), scaling.double().requires_grad_(True)
+    iv = sr[:, 0].view(-1, 1, 1, 1) * fr
+    iu = sr[:, 1].view(-1, 1, 1, 1) * fr
+    loss = (iv * gv.double()).sum() + (iu * gu.double()).sum()
+    if want_trunk:
+        tr = torch.cat([iv, iu]).permute(0, 2, 3, 1)
+        loss = loss + (tr * gt.double()).sum()
+    loss.backward()
+    fd, sd = feats.cuda().requires_grad_(True), scaling.cuda().requires_grad_(True)
+    a, b, t = ops.scale_pair(fd, sd, want_trunk=want_trunk)
+    l2 = (a * gv.cuda()).sum() + (b * gu.cuda()).sum()
+    if want_trunk:
+        assert t.dtype == torch.bfloat16 and t.shape == (2 * B, H, W, 32)
+        assert rel_l2(t.float().cpu(), torch.cat([iv, iu]).permute(0, 2, 3, 1).detach()) < 4e-3       # bf16 rounding
+        l2 = l2 + (t.float() * gt.cuda().float()).sum()
+    else:
+        assert t is None
+    l2.backward()
+    assert torch.equal(a.cpu(), (scaling[:, 0].view(-1, 1, 1, 1) * feats)) and torch.equal(b.cpu(), scaling[:, 1].view(-1, 1, 1, 1) * feats)
+    assert rel_l2(fd.grad.cpu(), fr.grad) < 1e-5
+    assert rel_l2(sd.grad.cpu(), sr.grad) < 1e-5
+
+
+def test_analytic_scaling_matches_reference():
+    from hdmoe_b200 import ops
+    t = torch.linspace(-2.0, 1.2, 37)
+    w = torch.sigmoid((t * 4 - (-1.2)) / 1.6)
+    ref = torch.stack([(w + 1e-2) * 2, ((1.0 - w) + 1e-2) * 2], dim=1)         # models/model_config2.py:244-249
+    got = ops.analytic_scaling(t.cuda(), -1.2, 1.6).cpu()
+    assert rel_l2(got, ref) < 1e-6

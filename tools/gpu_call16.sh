@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_parity.py -q --no-header -x 2>&1 | tail -5
+timeout 900 python bench.py --steps 10 --warmup 3 --no-sampler > gpurun_out/c16_bench.log 2> gpurun_out/c16_bench.err; echo "bench rc=$?"
+grep -v Warning gpurun_out/c16_bench.err | grep -v "run_backward\|^$" | tail -8
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/c16_bench.log').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'])
+PY

@@ -2,24 +2,12 @@
 import sys, collections, re, torch
 sys.path.insert(0, '.')
 import bench, hdmoe_b200
-from hdmoe_b200.utils import EDM_LOSS
 dev = torch.device("cuda")
 torch.backends.cuda.matmul.allow_tf32 = True
 torch.backends.cudnn.allow_tf32 = True
 hdmoe_b200.set_expert_dtype(torch.bfloat16)
-B = 256
-model = bench.build_model(1, dev); model.train()
-crit = EDM_LOSS(**bench.LOSS)
-params = list(model.parameters())
-opt = torch.optim.AdamW(params, lr=5e-4, fused=True)
-b = {k: v.to(dev) for k, v in bench.synth_batch(B, 32, 0, dev).items()}
-def step():
-    out = model(x=b["x"], sigma=b["sigma"], text_emb=b["text"], Unet_router_mask=b["um"], Vit_router_mask=b["vm"], zeta=2.0, return_log_var=True)
-    loss = crit(b["sigma"], b["x0"], b["sigma"], out)
-    opt.zero_grad(set_to_none=True)
-    loss["loss"].backward()
-    torch.nn.utils.clip_grad_norm_(params, 1.0)
-    opt.step()
+r = bench.TrainRunner(1, 32, 256, 0, 1, dev, "dp", use_graph=False, warmup=0)     # bench.py's step, eager
+step = lambda: r.eager_step(r.dev_batch)
 for _ in range(3): step()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
@@ -42,5 +30,5 @@ for e in ka:
     if t is None: t = e.self_cuda_time_total
     if t > 0: rows.append((t, e.count, e.key, str(e.input_shapes)[:90]))
 rows.sort(reverse=True)
-for t, c, k, sh in rows[:45]:
+for t, c, k, sh in rows[:int(sys.argv[1]) if len(sys.argv) > 1 else 45]:
     print(f"{t/1e3:8.3f} ms n={c:4d} {k:38s} {sh}")

@@ -3,28 +3,13 @@ prints per-bin concurrency and the dominant kernels, to find the critical path. 
 import sys, collections, re, torch
 sys.path.insert(0, '.')
 import bench, hdmoe_b200
-from hdmoe_b200.utils import EDM_LOSS
-from hdmoe_b200.train_step import GraphedTrainStep
 from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda")
 torch.backends.cuda.matmul.allow_tf32 = True
 torch.backends.cudnn.allow_tf32 = True
 hdmoe_b200.set_expert_dtype(torch.bfloat16)
-B = 256
-model = bench.build_model(1, dev); model.train()
-crit = EDM_LOSS(**bench.LOSS)
-params = list(model.parameters())
-opt = torch.optim.AdamW(params, lr=5e-4, fused=True, capturable=True)
-b = {k: v.to(dev) for k, v in bench.synth_batch(B, 32, 0, dev).items()}
-def step(b):
-    out = model(x=b["x"], sigma=b["sigma"], text_emb=b["text"], Unet_router_mask=b["um"], Vit_router_mask=b["vm"], zeta=2.0, return_log_var=True)
-    loss = crit(b["sigma"], b["x0"], b["sigma"], out)
-    opt.zero_grad(set_to_none=True)
-    loss["loss"].backward()
-    torch.nn.utils.clip_grad_norm_(params, 1.0)
-    opt.step()
-    return loss["loss"]
-g = GraphedTrainStep(step, b, warmup=3).capture()
+r = bench.TrainRunner(1, 32, 256, 0, 1, dev, "dp", use_graph=True, warmup=3)      # exactly bench.py's captured step
+g = r.graphed
 for _ in range(3): g(None)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
