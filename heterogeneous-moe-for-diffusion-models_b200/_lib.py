@@ -90,6 +90,8 @@ PROTOTYPES = {
     "hdmoe_scale_pair_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i64, _p]),
     "hdmoe_scale_pair_tiles": (_i, [_i64]),
     "hdmoe_scale_pair_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i64, _p]),
+    "hdmoe_scaling_router_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _f, _p, _i, _i, _p]),
+    "hdmoe_scaling_router_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "hdmoe_sqerr_rows": (_i, [_p, _p, _p, _i, _i64, _p]),
     "hdmoe_sqerr_rows_bwd": (_i, [_p, _p, _p, _p, _i, _i64, _p]),
     "hdmoe_optim_chunk_elems": (_i, []),

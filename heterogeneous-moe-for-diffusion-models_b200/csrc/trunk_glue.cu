@@ -505,3 +505,202 @@ extern "C" int hdmoe_scale_pair_bwd(const float* feats, const float* scaling, co
     HDMOE_CHECK_LAUNCH();
     return HDMOE_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ Scaling_router
+// models/model_components.py:41-66 (cfg1): x [B, D] -> W1 (D -> 2D) -> GroupNorm(1) -> ReLU -> W2 (2D -> 4D) ->
+// GroupNorm(1) -> ReLU -> Dropout -> W3 (4D -> 2) -> + zeta * noise -> softmax * 2.  ~25 small launches forward and ~50
+// backward in the op-by-op version; here one CTA per sample does the whole chain (D = 64: 41 k weights, L2 resident),
+// the backward recomputes it and accumulates the weight / affine gradients with atomics.
+namespace hdmoe {
+constexpr int kSrD = 64, kSrH1 = 128, kSrH2 = 256, kSrT = 256;
+
+__device__ __forceinline__ float sr_block_sum(float v, float* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSrT / 32; ++i) t += red[i];
+    return t;
+}
+
+struct SrShared {
+    float x[kSrD], h1[kSrH1], y1[kSrH1], h2[kSrH2], y2[kSrH2], red[8];
+    float mu1, rs1, mu2, rs2, l[2];
+};
+
+// forward of one sample into shared memory; returns the two logits in s.l (before noise)
+__device__ __forceinline__ void sr_forward(SrShared& s, const float* __restrict__ xb, const float* __restrict__ W1,
+                                           const float* __restrict__ g1, const float* __restrict__ b1,
+                                           const float* __restrict__ W2, const float* __restrict__ g2,
+                                           const float* __restrict__ b2, const float* __restrict__ W3,
+                                           const float* __restrict__ keep, float eps) {
+    const int t = threadIdx.x;
+    if (t < kSrD) s.x[t] = xb[t];
+    __syncthreads();
+    float h = 0.f;
+    if (t < kSrH1) {
+        const float4* w = reinterpret_cast<const float4*>(W1 + (size_t)t * kSrD);
+#pragma unroll 4
+        for (int k = 0; k < kSrD / 4; ++k) {
+            const float4 q = w[k];
+            h += q.x * s.x[4 * k] + q.y * s.x[4 * k + 1] + q.z * s.x[4 * k + 2] + q.w * s.x[4 * k + 3];
+        }
+        s.h1[t] = h;
+    }
+    float m = sr_block_sum(t < kSrH1 ? h : 0.f, s.red) / kSrH1;
+    float d = t < kSrH1 ? h - m : 0.f;
+    float var = sr_block_sum(d * d, s.red) / kSrH1;
+    if (t == 0) {
+        s.mu1 = m;
+        s.rs1 = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    if (t < kSrH1) s.y1[t] = fmaxf((h - s.mu1) * s.rs1 * g1[t] + b1[t], 0.f);
+    __syncthreads();
+    {
+        const float4* w = reinterpret_cast<const float4*>(W2 + (size_t)t * kSrH1);
+        h = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < kSrH1 / 4; ++k) {
+            const float4 q = w[k];
+            h += q.x * s.y1[4 * k] + q.y * s.y1[4 * k + 1] + q.z * s.y1[4 * k + 2] + q.w * s.y1[4 * k + 3];
+        }
+        s.h2[t] = h;
+    }
+    m = sr_block_sum(h, s.red) / kSrH2;
+    d = h - m;
+    var = sr_block_sum(d * d, s.red) / kSrH2;
+    if (t == 0) {
+        s.mu2 = m;
+        s.rs2 = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    float y = fmaxf((h - s.mu2) * s.rs2 * g2[t] + b2[t], 0.f);
+    if (keep) y *= keep[t];
+    s.y2[t] = y;
+    const float l0 = sr_block_sum(W3[t] * y, s.red), l1 = sr_block_sum(W3[kSrH2 + t] * y, s.red);
+    if (t == 0) {
+        s.l[0] = l0;
+        s.l[1] = l1;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSrT)
+scaling_router_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ g1,
+                          const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ g2,
+                          const float* __restrict__ b2, const float* __restrict__ W3, const float* __restrict__ noise,
+                          float zeta, const float* __restrict__ keep, float eps, float* __restrict__ out) {
+    __shared__ SrShared s;
+    const int b = blockIdx.x;
+    sr_forward(s, x + (size_t)b * kSrD, W1, g1, b1, W2, g2, b2, W3, keep ? keep + (size_t)b * kSrH2 : nullptr, eps);
+    if (threadIdx.x == 0) {
+        float l0 = s.l[0], l1 = s.l[1];
+        if (noise) {
+            l0 += noise[2 * b] * zeta;
+            l1 += noise[2 * b + 1] * zeta;
+        }
+        const float m = fmaxf(l0, l1), e0 = expf(l0 - m), e1 = expf(l1 - m), inv = 2.f / (e0 + e1);
+        out[2 * b] = e0 * inv;
+        out[2 * b + 1] = e1 * inv;
+    }
+}
+
+// GroupNorm(1) backward of one layer held in shared memory: dy (gradient w.r.t. the post-ReLU output, dropout already
+// applied) -> dh in place; accumulates dgamma / dbeta
+__device__ __forceinline__ float sr_gn_bwd(float dy, float h, float y_pos, float mu, float rs, float gamma, int n, bool live,
+                                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* red) {
+    const float xh = (h - mu) * rs;
+    const float dyn = (live && y_pos > 0.f) ? dy : 0.f;          // ReLU
+    if (live) {
+        atomicAdd(dgamma, dyn * xh);
+        atomicAdd(dbeta, dyn);
+    }
+    const float g = dyn * gamma;
+    const float m1 = sr_block_sum(g, red) / n, m2 = sr_block_sum(g * xh, red) / n;
+    return live ? rs * (g - m1 - xh * m2) : 0.f;
+}
+
+__global__ void __launch_bounds__(kSrT)
+scaling_router_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ g1,
+                          const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ g2,
+                          const float* __restrict__ b2, const float* __restrict__ W3, const float* __restrict__ noise,
+                          float zeta, const float* __restrict__ keep, float eps, const float* __restrict__ d_out,
+                          float* __restrict__ dx, float* __restrict__ dW1, float* __restrict__ dg1, float* __restrict__ db1,
+                          float* __restrict__ dW2, float* __restrict__ dg2, float* __restrict__ db2, float* __restrict__ dW3) {
+    __shared__ SrShared s;
+    __shared__ float dh2[kSrH2], dh1[kSrH1];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const float* kp = keep ? keep + (size_t)b * kSrH2 : nullptr;
+    sr_forward(s, x + (size_t)b * kSrD, W1, g1, b1, W2, g2, b2, W3, kp, eps);
+    float l0 = s.l[0], l1 = s.l[1];
+    if (noise) {
+        l0 += noise[2 * b] * zeta;
+        l1 += noise[2 * b + 1] * zeta;
+    }
+    const float m = fmaxf(l0, l1), e0 = expf(l0 - m), e1 = expf(l1 - m), inv = 1.f / (e0 + e1);
+    const float p0 = e0 * inv, p1 = e1 * inv;
+    const float go0 = d_out[2 * b], go1 = d_out[2 * b + 1];
+    const float dot = p0 * go0 + p1 * go1;
+    const float dl0 = 2.f * p0 * (go0 - dot), dl1 = 2.f * p1 * (go1 - dot);     // out = 2 * softmax(l)
+    // W3 and the input of W3 (y2 includes the dropout scaling)
+    atomicAdd(dW3 + t, dl0 * s.y2[t]);
+    atomicAdd(dW3 + kSrH2 + t, dl1 * s.y2[t]);
+    float dy2 = W3[t] * dl0 + W3[kSrH2 + t] * dl1;
+    if (kp) dy2 *= kp[t];
+    // undo the dropout factor for the ReLU test: y2 > 0 iff the pre-dropout activation > 0 (or the unit was dropped: dy2 = 0 then)
+    const float pre2 = (s.h2[t] - s.mu2) * s.rs2 * g2[t] + b2[t];
+    dh2[t] = sr_gn_bwd(dy2, s.h2[t], pre2, s.mu2, s.rs2, g2[t], kSrH2, true, dg2 + t, db2 + t, s.red);
+    __syncthreads();
+    // dW2[j][k] += dh2[j] * y1[k]: thread t owns column block: loop over rows j, coalesced over k
+    for (int j = 0; j < kSrH2; ++j) {
+        const float dj = dh2[j];
+        if (t < kSrH1 && dj != 0.f) atomicAdd(dW2 + (size_t)j * kSrH1 + t, dj * s.y1[t]);
+    }
+    float dy1 = 0.f;
+    if (t < kSrH1)
+        for (int j = 0; j < kSrH2; ++j) dy1 = fmaf(W2[(size_t)j * kSrH1 + t], dh2[j], dy1);
+    const bool live1 = t < kSrH1;
+    const float pre1 = live1 ? (s.h1[t] - s.mu1) * s.rs1 * g1[t] + b1[t] : 0.f;
+    const float d1 = sr_gn_bwd(dy1, live1 ? s.h1[t] : 0.f, pre1, s.mu1, s.rs1, live1 ? g1[t] : 0.f, kSrH1, live1,
+                               dg1 + (live1 ? t : 0), db1 + (live1 ? t : 0), s.red);
+    if (live1) dh1[t] = d1;
+    __syncthreads();
+    for (int j = 0; j < kSrH1; ++j) {
+        const float dj = dh1[j];
+        if (t < kSrD && dj != 0.f) atomicAdd(dW1 + (size_t)j * kSrD + t, dj * s.x[t]);
+    }
+    if (t < kSrD) {
+        float a = 0.f;
+        for (int j = 0; j < kSrH1; ++j) a = fmaf(W1[(size_t)j * kSrD + t], dh1[j], a);
+        dx[(size_t)b * kSrD + t] = a;
+    }
+}
+}  // namespace hdmoe
+
+extern "C" int hdmoe_scaling_router_fwd(const float* x, const float* W1, const float* g1, const float* b1, const float* W2,
+                                        const float* g2, const float* b2, const float* W3, const float* noise, float zeta,
+                                        const float* keep, float eps, float* out, int B, int D, hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(x && W1 && g1 && b1 && W2 && g2 && b2 && W3 && out && B >= 1, "scaling_router_fwd: null pointer");
+    HDMOE_CHECK_ARG(D == hdmoe::kSrD, "scaling_router_fwd: emb_dim must be %d (got %d)", hdmoe::kSrD, D);
+    hdmoe::scaling_router_fwd_kernel<<<B, hdmoe::kSrT, 0, (cudaStream_t)stream>>>(x, W1, g1, b1, W2, g2, b2, W3, noise, zeta, keep,
+                                                                                 eps, out);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_scaling_router_bwd(const float* x, const float* W1, const float* g1, const float* b1, const float* W2,
+                                        const float* g2, const float* b2, const float* W3, const float* noise, float zeta,
+                                        const float* keep, float eps, const float* d_out, float* dx, float* dW1, float* dg1,
+                                        float* db1, float* dW2, float* dg2, float* db2, float* dW3, int B, int D,
+                                        hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(x && W1 && g1 && b1 && W2 && g2 && b2 && W3 && d_out && dx && dW1 && dg1 && db1 && dW2 && dg2 && db2 && dW3 &&
+                        B >= 1, "scaling_router_bwd: null pointer");
+    HDMOE_CHECK_ARG(D == hdmoe::kSrD, "scaling_router_bwd: emb_dim must be %d (got %d)", hdmoe::kSrD, D);
+    hdmoe::scaling_router_bwd_kernel<<<B, hdmoe::kSrT, 0, (cudaStream_t)stream>>>(x, W1, g1, b1, W2, g2, b2, W3, noise, zeta, keep,
+                                                                                 eps, d_out, dx, dW1, dg1, db1, dW2, dg2, db2, dW3);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}

@@ -17,6 +17,13 @@ _CHANNELS_LAST = [False]   # measured: no gain on B200 (cuDNN picks NHWC kernels
 _FUSED_TRUNK = [True]       # fused GroupNorm(1)+ReLU(+pool) kernels and channels-last convolutions in Router.hard_route
 
 
+_FUSED_SCALING = [True]     # Scaling_router as one kernel per direction (csrc/trunk_glue.cu)
+
+
+def set_fused_scaling_router(enabled: bool) -> None:
+    _FUSED_SCALING[0] = bool(enabled)
+
+
 def set_router_fused_trunk(enabled: bool) -> None:
     _FUSED_TRUNK[0] = bool(enabled)
 
@@ -41,9 +48,32 @@ class Scaling_router(nn.Module):
         )
         self.linear = m.MP_Conv(in_channels=emb_dim * 4, out_channels=num_experts, kernel=())
 
+    def _fused_ok(self, x) -> bool:
+        sr = self.soft_route
+        return (_FUSED_SCALING[0] and x.is_cuda and x.dtype == torch.float32 and x.ndim == 2 and x.shape[1] == 64
+                and tuple(sr[0].weights.shape) == (128, 64) and tuple(sr[3].weights.shape) == (256, 128)
+                and tuple(self.linear.weights.shape) == (2, 256) and sr[1].num_groups == 1 and sr[4].num_groups == 1
+                and sr[1].eps == sr[4].eps)
+
     def forward(self, x: torch.Tensor, zeta: Optional[float] = 1e-2, noise: Optional[torch.Tensor] = None):
         if x.ndim == 3:
             x = x.squeeze(1)
+        if self._fused_ok(x):
+            # the whole chain (two MP linears + GroupNorm(1) + ReLU, dropout mask, logits, exploration noise, softmax * 2)
+            # as ONE kernel forward and one backward (csrc/trunk_glue.cu) on the prepared weights
+            sr, B = self.soft_route, x.shape[0]
+            W1 = sr[0].prepared_weight(1.0, torch.float32)
+            W2 = sr[3].prepared_weight(1.0, torch.float32)
+            W3 = self.linear.prepared_weight(1.0, torch.float32)
+            keep = None
+            p = sr[6].p
+            if self.training and p > 0:
+                keep = (torch.rand(B, 256, device=x.device) >= p).float() / (1.0 - p)
+            nz = None
+            if self.training:
+                nz = torch.randn(B, 2, device=x.device) if noise is None else noise
+            return ops.scaling_router(x, W1, sr[1].weight, sr[1].bias, W2, sr[4].weight, sr[4].bias, W3, noise=nz,
+                                      zeta=float(zeta), keep=keep, eps=sr[1].eps)
         x = self.linear(self.soft_route(x))
         if self.training:
             x = x + (torch.randn_like(x) if noise is None else noise) * zeta

@@ -587,7 +587,7 @@ def get_gconv_impl() -> int:
     return _GCONV_IMPL[0]
 
 
-_GCONV3_VALIDATED = False
+_GCONV3_VALIDATED = True       # passes tests/test_gpu_gconv.py on B200 (round 2); not the default: see profiles/r2_gconv_shapes.md
 
 
 def gconv_wgrad_raw(x, dy, dw, row_expert, n_rows_dev, ksizes, wrows):
@@ -937,3 +937,46 @@ def scale_pair(feats, scaling, want_trunk: bool = False):
     """(in_vit, in_unet, trunk_in): scaling[b, 0] * feats, scaling[b, 1] * feats (fp32 [B, C, H, W]) and optionally the
     channels-last bf16 copy [2B, H, W, C] of both for the tcgen05 router trunk -- one pass over feats."""
     return _ScalePair.apply(feats, scaling, want_trunk)
+
+
+# ----------------------------------------------------------------------------------------------------
+# (12) Scaling_router (cfg1) as one kernel per direction (csrc/trunk_glue.cu)
+# ----------------------------------------------------------------------------------------------------
+class _ScalingRouter(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W1, g1, b1, W2, g2, b2, W3, noise, zeta, keep, eps):
+        _cuda(x, W1, g1, b1, W2, g2, b2, W3, noise, keep)
+        shapes = [tuple(t.shape) for t in (W1, g1, b1, W2, g2, b2, W3)]
+        x, W1, g1, b1, W2, g2, b2, W3 = (_f32c(t) for t in (x, W1, g1, b1, W2, g2, b2, W3))
+        noise, keep = _f32c(noise), _f32c(keep)
+        B, D = x.shape
+        if W1.numel() != 2 * D * D or W2.numel() != 8 * D * D or W3.numel() != 8 * D:
+            raise RuntimeError("scaling_router: weights must be [2D, D], [4D, 2D], [2, 4D]")
+        out = torch.empty(B, 2, dtype=torch.float32, device=x.device)
+        L.check(L.lib().hdmoe_scaling_router_fwd(_p(x), _p(W1), _p(g1), _p(b1), _p(W2), _p(g2), _p(b2), _p(W3), _p(noise),
+                                                 float(zeta), _p(keep), float(eps), _p(out), B, D, _st()),
+                "scaling_router_fwd")
+        ctx.save_for_backward(x, W1, g1, b1, W2, g2, b2, W3, noise, keep)
+        ctx.meta = (float(zeta), float(eps), shapes)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, W1, g1, b1, W2, g2, b2, W3, noise, keep = ctx.saved_tensors
+        zeta, eps, shapes = ctx.meta
+        B, D = x.shape
+        sizes = [W1.numel(), g1.numel(), b1.numel(), W2.numel(), g2.numel(), b2.numel(), W3.numel()]
+        acc = torch.zeros(sum(sizes), dtype=torch.float32, device=x.device)
+        parts = list(acc.split(sizes))
+        dx = torch.empty_like(x)
+        L.check(L.lib().hdmoe_scaling_router_bwd(_p(x), _p(W1), _p(g1), _p(b1), _p(W2), _p(g2), _p(b2), _p(W3), _p(noise), zeta,
+                                                 _p(keep), eps, _p(_f32c(d_out)), _p(dx), _p(parts[0]), _p(parts[1]),
+                                                 _p(parts[2]), _p(parts[3]), _p(parts[4]), _p(parts[5]), _p(parts[6]), B, D,
+                                                 _st()), "scaling_router_bwd")
+        grads = [p_.view(sh) for p_, sh in zip(parts, shapes)]
+        return (dx, *grads, None, None, None, None)
+
+
+def scaling_router(x, W1, g1, b1, W2, g2, b2, W3, noise=None, zeta: float = 0.0, keep=None, eps: float = 1e-5):
+    """Scaling_router.forward on prepared weights (see include/hdmoe_b200.h); x [B, 64] -> [B, 2] = softmax * 2."""
+    return _ScalingRouter.apply(x, W1, g1, b1, W2, g2, b2, W3, noise, zeta, keep, eps)

@@ -370,6 +370,20 @@ int hdmoe_scale_pair_bwd(const float* feats, const float* scaling, const float* 
                          const void* g_trunk_bf16, float* d_feats, float* ds_part, int B, int C, int64_t HW,
                          hdmoe_stream_t stream);
 
+/* Scaling_router.forward (models/model_components.py:41-66, model_config1) as one kernel per direction:
+ *   x [B, 64] -> W1 [128, 64] -> GroupNorm(1, 128) (g1, b1) -> ReLU -> W2 [256, 128] -> GroupNorm(1, 256) (g2, b2) -> ReLU
+ *   -> * keep [B, 256] (dropout mask already divided by 1 - p; NULL = no dropout) -> W3 [2, 256] -> + zeta * noise [B, 2]
+ *   (NULL in eval) -> softmax * 2 -> out [B, 2].  W1..W3 are the PREPARED MP_Conv weights.  The backward recomputes
+ *   the forward and ACCUMULATES dW1, dg1, db1, dW2, dg2, db2, dW3 (zero them first); dx [B, 64] is written. */
+int hdmoe_scaling_router_fwd(const float* x, const float* W1, const float* g1, const float* b1, const float* W2,
+                             const float* g2, const float* b2, const float* W3, const float* noise, float zeta,
+                             const float* keep, float eps, float* out, int B, int D, hdmoe_stream_t stream);
+int hdmoe_scaling_router_bwd(const float* x, const float* W1, const float* g1, const float* b1, const float* W2,
+                             const float* g2, const float* b2, const float* W3, const float* noise, float zeta,
+                             const float* keep, float eps, const float* d_out, float* dx, float* dW1, float* dg1,
+                             float* db1, float* dW2, float* dg2, float* db2, float* dW3, int B, int D,
+                             hdmoe_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (12) EDM_LOSS data term (Utils/utils.py:135-146): per-sample squared error se[b] = sum_i (D[b,i] - x0[b,i])^2 and its
  *      backward dD[b,i] = 2 (D - x0) g_se[b]; every image-dependent loss term is a function of se and the per-sample

@@ -109,3 +109,39 @@ def test_analytic_scaling_matches_reference():
     ref = torch.stack([(w + 1e-2) * 2, ((1.0 - w) + 1e-2) * 2], dim=1)         # models/model_config2.py:244-249
     got = ops.analytic_scaling(t.cuda(), -1.2, 1.6).cpu()
     assert rel_l2(got, ref) < 1e-6
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_scaling_router_fused_matches_oracle(train):
+    """Scaling_router.forward (models/model_components.py:41-66) as one kernel per direction against oracle.scaling_router
+    (fp64): output, input gradient, all weight / GroupNorm gradients; the module path (prepared weights, forced weight
+    norm in training) is what runs."""
+    from hdmoe_b200 import model_components as mc
+    torch.manual_seed(3)
+    sr = mc.Scaling_router(emb_dim=64, num_experts=2, dropout=0.0)
+    gen = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for i in (1, 4):
+            sr.soft_route[i].weight.copy_(1 + 0.2 * torch.randn(sr.soft_route[i].weight.shape, generator=gen))
+            sr.soft_route[i].bias.copy_(0.2 * torch.randn(sr.soft_route[i].bias.shape, generator=gen))
+    B = 37
+    x = torch.randn(B, 64, generator=gen)
+    nz = torch.randn(B, 2, generator=gen)
+    gy = torch.randn(B, 2, generator=gen)
+    sd = {"s." + k: v.detach().double().clone().requires_grad_(True) for k, v in sr.state_dict().items()}
+    xr = x.double().requires_grad_(True)
+    import contextlib
+    with (O.training_mode() if train else contextlib.nullcontext()):
+        ref = O.scaling_router(sd, "s.", xr, noise=nz.double() if train else None, zeta=0.7 if train else 0.0)
+    (ref * gy.double()).sum().backward()
+    sr.cuda().train(train)
+    xd = x.cuda().requires_grad_(True)
+    out = sr(xd, zeta=0.7, noise=nz.cuda())
+    (out * gy.cuda()).sum().backward()
+    assert rel_l2(out.cpu(), ref) < 1e-5
+    assert rel_l2(xd.grad.cpu(), xr.grad) < 2e-5
+    for k, p in sr.named_parameters():
+        assert rel_l2(p.grad.cpu(), sd["s." + k].grad) < 5e-5, k
+        if train and k.endswith("weights"):
+            assert rel_l2(p.detach().cpu(), sd["s." + k].detach()) < 1e-6, k        # forced weight norm (Q6)
+    assert torch.allclose(out.sum(1).cpu(), torch.full((B,), 2.0), atol=1e-5)      # rows sum to 2 (test_routers.py:28-29)
