@@ -356,11 +356,27 @@ class HDMOEM(nn.Module):
         s_unet = scaling[:, 1:2].view(-1, 1, 1, 1)
         # router trunks of both routers as grouped tcgen05 launches (bf16 configuration): pooled features up front
         trunk = self._router_trunk(x)
-        pool_vit = pool_un = None
+        pool_vit = pool_un = routed = None
         if glue:
             # one pass over feats: both scaled branch inputs and the channels-last bf16 router-trunk input
             in_vit, in_unet, trunk_in = ops.scale_pair(feats, scaling, want_trunk=trunk is not None)
-            if trunk is not None:
+            if trunk is not None and _BRANCH_STREAMS[0]:
+                # The trunk runs on its own stream so that its BACKWARD does too (autograd replays a node on the stream of
+                # its forward): the trunk's gradient only depends on the router-gate backward, which is available at the very
+                # start of the backward pass, while its result is consumed at the very end (scale_pair backward) -- inside
+                # the captured step the ~1.3 ms of trunk data / weight gradients become a graph branch beside the attention
+                # backward instead of a serial tail.
+                # The two router tails run on the same stream (ViT first: RNG order, quirk Q2): a gate backward on the main
+                # stream would be enqueued behind the whole expert backward and hold the trunk's gradient back.
+                with _fork(_streams(x.device, "trunk", 1)[0], (trunk_in, te, Vit_router_mask, Unet_router_mask)) as fkt:
+                    pool_vit, pool_un = trunk(None, self.training, pre_nhwc=trunk_in)
+                    routed = (self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
+                                              noise=noise.get("vit"), pooled=pool_vit),
+                              self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
+                                               noise=noise.get("unet"), pooled=pool_un))
+                fkt.join(*routed[0], *routed[1], *(self._topk_of(self.vit_router, x) or ()),
+                         *(self._topk_of(self.Unet_router, x) or ()))
+            elif trunk is not None:
                 pool_vit, pool_un = trunk(None, self.training, pre_nhwc=trunk_in)
         else:
             in_unet = s_unet * feats
@@ -371,10 +387,16 @@ class HDMOEM(nn.Module):
         if _BRANCH_STREAMS[0] and x.is_cuda and _EP["placement"] is None:
             # ViT branch (router + MoE layer) beside the U-Net branch; host program order as in the reference
             with _fork(_streams(x.device, "branch", 1)[0], (in_vit, te, text_emb, Vit_router_mask, pool_vit)) as fk:
-                w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
-                                                        noise=noise.get("vit"), pooled=pool_vit)
-            w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
-                                                  noise=noise.get("unet"), pooled=pool_un)
+                if routed is not None:
+                    w_vit, p_vit, raw_vit = routed[0]
+                else:
+                    w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
+                                                            noise=noise.get("vit"), pooled=pool_vit)
+            if routed is not None:
+                w_un, p_un, raw_un = routed[1]
+            else:
+                w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
+                                                      noise=noise.get("unet"), pooled=pool_un)
             tk_u, tk_v = self._topk_of(self.Unet_router, x), self._topk_of(self.vit_router, x)
             out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k, nhwc_out=glue,
                                            topk=tk_u)
@@ -383,10 +405,13 @@ class HDMOEM(nn.Module):
                                                nhwc_out=glue, topk=tk_v)
             fk.join(w_vit, p_vit, raw_vit, out_v)
         else:
-            w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
-                                                    noise=noise.get("vit"), pooled=pool_vit)
-            w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
-                                                  noise=noise.get("unet"), pooled=pool_un)
+            if routed is not None:
+                (w_vit, p_vit, raw_vit), (w_un, p_un, raw_un) = routed
+            else:
+                w_vit, p_vit, raw_vit = self.vit_router(x=in_vit, time_emb=te, zeta=zeta, mask=Vit_router_mask,
+                                                        noise=noise.get("vit"), pooled=pool_vit)
+                w_un, p_un, raw_un = self.Unet_router(x=in_unet, time_emb=te, zeta=zeta, mask=Unet_router_mask,
+                                                      noise=noise.get("unet"), pooled=pool_un)
             tk_u, tk_v = self._topk_of(self.Unet_router, x), self._topk_of(self.vit_router, x)
             out_u = router_to_unet_experts(in_unet, self.Unet_experts, w_un, te, text_emb, top_k=self.top_k, nhwc_out=glue,
                                            topk=tk_u)
