@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhdmoe_b200.so")
+# HDMOE_B200_LIB: another build of the same library (kernel A/B measurements in tools/); the product path is the in-tree one
+LIB_PATH = os.environ.get("HDMOE_B200_LIB") or os.path.join(_HERE, "lib", "libhdmoe_b200.so")
 
 F32, BF16 = 0, 1
 MAX_EXPERTS, MAX_TOPK = 64, 8

@@ -589,6 +589,51 @@ __device__ __forceinline__ void load_base(const TO* p, float (&v)[8]) {
     for (int q = 0; q < N; ++q) v[q] = to_f32<TO>(p[q]);
 }
 
+// K = 1 without a residual base (the reference's top-1 configuration): out[t] = rows[tok_rows[t]] * w.  Four independent
+// 16-byte row vectors in flight per thread -- index loads first, then the row loads, then the stores -- instead of the
+// generic kernel's dependent index -> weight -> row chain per vector.
+template <typename TR, typename TO>
+__global__ void __launch_bounds__(256)
+combine_k1_kernel(const TR* __restrict__ rows, const int32_t* __restrict__ tok_rows, const float* __restrict__ row_w,
+                  TO* __restrict__ out, int T, long long D, int vshift) {
+    constexpr int N = VecN<TR>::N, U = 4;
+    const long long vec_per_row = D / N;
+    const long long total = (long long)T * vec_per_row;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+        int t[U], r[U];
+        long long d[U];
+        float w[U], v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            t[u] = -1;
+            r[u] = -1;
+            if (i < total) {
+                t[u] = vshift >= 0 ? (int)(i >> vshift) : (int)(i / vec_per_row);
+                d[u] = (i - (long long)t[u] * vec_per_row) * N;
+                r[u] = __ldg(tok_rows + t[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            w[u] = (r[u] >= 0 && row_w) ? __ldg(row_w + r[u]) : 1.f;
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[u][q] = 0.f;
+            if (r[u] >= 0) VecN<TR>::load(rows + (long long)r[u] * D + d[u], v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (t[u] < 0) continue;
+            float acc[8];
+            // multiply, round, then add to zero (the reference does `out_e * w` then `+=` into zeros): no FMA contraction
+#pragma unroll
+            for (int q = 0; q < N; ++q) acc[q] = r[u] >= 0 ? __fadd_rn(0.f, __fmul_rn(v[u][q], w[u])) : 0.f;
+            store_n<TO, N>(out + (long long)t[u] * D + d[u], acc);
+        }
+    }
+}
+
 template <typename TR, typename TO>
 __global__ void __launch_bounds__(256)
 combine_kernel(const TR* __restrict__ rows, const int32_t* __restrict__ tok_rows, const float* __restrict__ row_w,
@@ -801,8 +846,12 @@ static int launch_combine(const void* rows, const int32_t* tok_rows, const float
     int vshift = -1;
     for (int b = 0; b < 31; ++b)
         if ((1ll << b) == vpr) vshift = b;
-    combine_kernel<TR, TO><<<grid_for(total, 512, 16), 256, 0, st>>>((const TR*)rows, tok_rows, row_w, (const TO*)base,
-                                                                    (TO*)out, T, K, D, vshift);
+    if (K == 1 && !base)
+        combine_k1_kernel<TR, TO><<<grid_for(total, 1024, 8), 256, 0, st>>>((const TR*)rows, tok_rows, row_w, (TO*)out, T, D,
+                                                                            vshift);
+    else
+        combine_kernel<TR, TO><<<grid_for(total, 512, 16), 256, 0, st>>>((const TR*)rows, tok_rows, row_w, (const TO*)base,
+                                                                        (TO*)out, T, K, D, vshift);
     HDMOE_CHECK_LAUNCH();
     return HDMOE_OK;
 }

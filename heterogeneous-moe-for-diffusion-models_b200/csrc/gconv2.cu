@@ -33,6 +33,7 @@ namespace hdmoe {
 
 #ifdef HDMOE_G2_TRACE
 __device__ long long g2_trace[148 * 64];
+__device__ long long g2_span[148 * 2];          // globaltimer at kernel entry / exit of every CTA
 __device__ __forceinline__ long long g2_gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define G2T(slot) do { if (blockIdx.x < 148 && tcount < 8) { g2_trace[blockIdx.x * 64 + tcount * 8 + (slot)] = clock64(); \
     if ((slot) == 0) g2_trace[blockIdx.x * 64 + tcount * 8 + 6] = g2_gtime(); if ((slot) == 5) g2_trace[blockIdx.x * 64 + tcount * 8 + 7] = g2_gtime(); } } while (0)
@@ -54,6 +55,7 @@ struct GConv2Params {
     int upt;                          // channel chunks of KC per tap
     int n_experts;
     int a_stage_bytes;                // bytes of one halo buffer
+    int b_stages;                     // depth of the weight ring (4 .. kG2BStagesMax)
     const int32_t* row_expert;
     const int32_t* n_rows_dev;
     __nv_bfloat16* Y;
@@ -74,15 +76,35 @@ struct G2Tile {
     int mt_n, p0, h0, c0;             // M-tiles, first position, its image row / offset inside that row's box
 };
 
+// weight ring: four stages, deepened (launch parameter b_stages) until it holds HDMOE_G2_RING_BYTES when the halo
+// buffers leave room -- the small stages of Cout = 32 / KC = 32 otherwise cover less than one TMA round trip of MMAs
+#ifndef HDMOE_G2_RING_BYTES
+#define HDMOE_G2_RING_BYTES 65536
+#endif
+constexpr int kG2BStagesMax = 16;
+constexpr int g2_b_stages(int b_stage_bytes) {
+    int n = HDMOE_G2_RING_BYTES / b_stage_bytes;
+    return n < 4 ? 4 : (n > kG2BStagesMax ? kG2BStagesMax : n);
+}
+
+// filter taps per weight stage (one TMA box of TPS * N rows): stages of ~16 KiB, so that the producer's per-stage work
+// (barrier wait, expect_tx, TMA issue from a single lane) is spread over >= 8 MMAs per issuer also at Cout = 32 / KC = 32
+constexpr int g2_tps(int kc, int n) {
+    int t = 16384 / (n * kc * 2);
+    t = t < 1 ? 1 : (t > 4 ? 4 : t);
+    while (t > 1 && t * n > 256) --t;
+    return t;
+}
+
 template <int KC, int N>
 struct Conv2Cfg {
     static constexpr int MT_MAX = N <= 64 ? 3 : 2;             // M-tiles (of 128 positions) per strip (<= kG2Issuers)
     static constexpr int ROWB = KC * 2;                        // bytes per position
-    static constexpr int TPS = N <= 64 ? 2 : 1;                // filter taps per weight stage (one TMA box of TPS*N rows)
+    static constexpr int TPS = g2_tps(KC, N);
     static constexpr int B_TAP = N * KC * 2;                   // bytes of one tap's [N x KC] weight tile
     static constexpr int B_STAGE = TPS * B_TAP;
     static constexpr int A_STAGES = 2;
-    static constexpr int B_STAGES = 4;
+    static constexpr int B_STAGES_MIN = 4;
     static constexpr int EPI_NB = (N % 64 == 0) ? 2 : 1;      // 32-column accumulator loads in flight per epilogue thread
     static constexpr int TMEM_NEED = 2 * MT_MAX * N;
     static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
@@ -174,18 +196,26 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
                   const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GConv2Params p) {
     using Cfg = Conv2Cfg<KC, N>;
     extern __shared__ uint8_t smem_raw[];
+#ifdef HDMOE_G2_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 148) g2_span[blockIdx.x * 2] = g2_gtime();
+#endif
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_buf = smem;                                              // A_STAGES halo buffers
     uint8_t* b_buf = smem + (size_t)Cfg::A_STAGES * p.a_stage_bytes;    // weight ring
-    __shared__ __align__(8) uint64_t a_full[Cfg::A_STAGES], a_empty[Cfg::A_STAGES], b_full[Cfg::B_STAGES],
-        b_empty[Cfg::B_STAGES], t_full[2], t_empty[2], q_full[kG2Queue], q_empty[kG2Queue];
+    __shared__ __align__(8) uint64_t a_full[Cfg::A_STAGES], a_empty[Cfg::A_STAGES], b_full[kG2BStagesMax],
+        b_empty[kG2BStagesMax], t_full[2], t_empty[2], q_full[kG2Queue], q_empty[kG2Queue];
+    const int BS = p.b_stages;
     __shared__ int32_t tile_q[kG2Queue];
+    // what the MMA issuers need of a tile, decoded once by the producer: kernel size (0 = not a compute tile), padded
+    // width, offset of the first position inside its box row, M-tiles
+    __shared__ int4 tile_geo[kG2Queue];
     __shared__ uint32_t tmem_base_s;
     // expert of every row, staged once: each role decodes every tile, and a global load per tile (~700 cycles of L2
     // latency in front of the first MMA of the tile) showed up as a 1 100-cycle gap between tiles
     __shared__ int8_t row_e_s[kG2RowCache];
     const int cap_rows = p.n_tiles / p.smax;
     const bool rows_cached = cap_rows <= kG2RowCache;
+    const int n_rows = *p.n_rows_dev;                  // requested first: its L2 round trip overlaps the whole set-up
     if (rows_cached)
         for (int r = threadIdx.x; r < cap_rows; r += kG2Threads) {
             const int e = p.row_expert[r];
@@ -198,25 +228,32 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&ta1) : "memory");
     }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::A_STAGES; ++s) {
-            mb_init(&a_full[s], 1);
-            mb_init(&a_empty[s], kG2Issuers);
+    // barrier set-up spread over the threads of warps 0, 2 and 3 (48+ serial mbarrier.init by one thread were ~1 000
+    // cycles of every CTA's prologue)
+    {
+        const int x = threadIdx.x;
+        bool did = false;
+        if (x < kG2Queue) {
+            mb_init(&q_full[x], 1);
+            mb_init(&q_empty[x], kG2Issuers + 4);
+            did = true;
+        } else if (x >= 64 && x < 64 + BS) {
+            mb_init(&b_full[x - 64], 1);
+            mb_init(&b_empty[x - 64], kG2Issuers);
+            did = true;
+        } else if (x >= 96 && x < 96 + Cfg::A_STAGES) {
+            mb_init(&a_full[x - 96], 1);
+            mb_init(&a_empty[x - 96], kG2Issuers);
+            did = true;
+        } else if (x >= 100 && x < 102) {
+            mb_init(&t_full[x - 100], kG2Issuers);
+            mb_init(&t_empty[x - 100], 4);
+            did = true;
         }
-        for (int s = 0; s < Cfg::B_STAGES; ++s) {
-            mb_init(&b_full[s], 1);
-            mb_init(&b_empty[s], kG2Issuers);
+        if (did) {
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-        for (int a = 0; a < 2; ++a) {
-            mb_init(&t_full[a], kG2Issuers);
-            mb_init(&t_empty[a], 4);
-        }
-        for (int s = 0; s < kG2Queue; ++s) {
-            mb_init(&q_full[s], 1);
-            mb_init(&q_empty[s], kG2Issuers + 4);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(&tmem_base_s)),
@@ -227,7 +264,6 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const int n_rows = *p.n_rows_dev;
 
     // tile id -> geometry.  Row-major with the rows reversed: the heavy (large-kernel) experts sit at the end of the
     // expert-major row order and are handed out first (longest-processing-time-first for the dynamic scheduler).
@@ -296,6 +332,7 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
                     if (ok || i < 0 || to.r >= n_rows || to.e < 0) {
                         mb_wait(&q_empty[qs], qph ^ 1);
                         tile_q[qs] = i;
+                        tile_geo[qs] = ok ? make_int4(p.ksize[to.kc], p.wp[to.kc], to.c0, to.mt_n) : make_int4(0, 0, 0, 0);
                         mb_arrive(&q_full[qs]);
                         if (++qs == kG2Queue) {
                             qs = 0;
@@ -304,6 +341,14 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
                     }
                     if (i < 0) {
                         more = false;
+                        // this CTA draws no more tiles: the last CTA to get here re-arms the scheduler for the next
+                        // launch on this stream (done now, under the remaining tiles, not in the kernel's tail)
+                        __threadfence();
+                        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+                            p.sched[0] = 0;
+                            p.sched[1] = 0;
+                            __threadfence();
+                        }
                         break;
                     }
                     if (ok) {
@@ -329,7 +374,7 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
                 const int k = p.ksize[cur.kc], taps = k * k;
                 const int wrow = p.wrow[cur.e];
                 const int nst = (taps + Cfg::TPS - 1) / Cfg::TPS;
-                const int pre = nst - 1 < Cfg::B_STAGES ? nst - 1 : Cfg::B_STAGES;
+                const int pre = nst - 1 < BS ? nst - 1 : BS;
                 bool have_next = false;
                 for (int s = 0; s < nst; ++s) {
                     if (s == pre) {
@@ -341,7 +386,7 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
                     // TPS consecutive taps are TPS*N consecutive rows of the tap-major weight block: one box
                     // (a trailing odd tap drags in N rows of the next block / OOB zeros; they are not used)
                     tma_load_2d(b_buf + (size_t)bs * Cfg::B_STAGE, &tmap_b, &b_full[bs], cur_c * KC, wrow + s * Cfg::TPS * N);
-                    if (++bs == Cfg::B_STAGES) {
+                    if (++bs == BS) {
                         bs = 0;
                         bph ^= 1;
                     }
@@ -353,73 +398,120 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
         }
     } else if (warp <= kG2Issuers) {
         // ============================== MMA issuers (warp w owns M-tile w-1) ==============================
+        // The WHOLE warp runs this loop converged and one elected lane issues.  Tile geometry is made warp-uniform with
+        // redux (`uni`), so descriptors and barrier addresses live in uniform registers: a loop entered by a single
+        // lane makes the compiler wrap every UTCHMMA in an ELECT + 3 x R2UR + branch waterfall and keeps the
+        // descriptor arithmetic on the vector datapath (~135-160 cycles per MMA per issuing thread, measured: the
+        // kernel ran at 59 / 68 / 82 cycles per MMA at (N, KC) = (64, 64) / (32, 64) / (32, 32), i.e. issue-bound,
+        // against the 48 / 40 / 40 cycles of the shared-memory operand feed).
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
                                    ((uint32_t)(128 >> 4) << 24);
-        const int mt = warp - 1;
+        const int mt = uni(warp) - 1;
         int tcount = 0;
         (void)tcount;
         int as = 0, bs = 0, acc = 0;
         uint32_t aph = 0, bph = 0, acc_ph = 0;
-        for (; lane == 0;) {
-            const int i = next_tile(false);
-            if (i < 0) break;
-            G2Tile t;
-            if (!tile_at(i, t)) continue;
-            const int k = p.ksize[t.kc], Wp = p.wp[t.kc], taps = k * k;
-            const bool active = mt < t.mt_n;
-            if (mt == 0) G2T(0);
+        // The producer publishes every tile with its geometry already decoded (tile_geo): re-deriving it here (constant-
+        // bank table reads, two divisions) left the tensor pipe idle for ~1 000 cycles between tiles.
+        struct TileU { int i, k, Wp, c0, active; };
+        auto fetch = [&]() -> TileU {
+            TileU u{-1, 0, 0, 0, 0};
+            for (;;) {
+                mb_wait(&q_full[qs], qph);
+                const int i = tile_q[qs];
+                const int4 g = tile_geo[qs];
+                __syncwarp();
+                if (lane == 0) mb_arrive(&q_empty[qs]);
+                if (++qs == kG2Queue) {
+                    qs = 0;
+                    qph ^= 1;
+                }
+                u.i = uni(i);
+                if (u.i < 0) return u;
+                u.k = uni(g.x);
+                if (u.k == 0) continue;                    // zero-fill entries of unused rows: the epilogue's business
+                u.Wp = uni(g.y);
+                u.c0 = uni(g.z);
+                u.active = uni((int)(mt < g.w));
+                return u;
+            }
+        };
+        TileU nx = fetch();
+        for (;;) {
+            if (nx.i < 0) break;
+            const int k = nx.k, Wp = nx.Wp, taps = k * k, c0u = nx.c0;
+            const bool active = nx.active != 0;
+            if (mt == 0 && lane == 0) G2T(0);
             mb_wait(&t_empty[acc], acc_ph ^ 1);
             tc_fence_after();
-            if (mt == 0) G2T(1);
+            if (mt == 0 && lane == 0) G2T(1);
             const uint32_t d = tmem_base + (uint32_t)((acc * Cfg::MT_MAX + mt) * N);
             for (int c = 0; c < p.upt; ++c) {
                 mb_wait(&a_full[as], aph);
                 tc_fence_after();
-                if (mt == 0 && c == 0) G2T(2);
+                if (mt == 0 && c == 0 && lane == 0) G2T(2);
                 // descriptor of this M-tile's first position; taps / k-slices only add to the 14-bit address field
                 const uint64_t a_desc0 =
-                    umma_desc<KC>(s2u(a_buf + (size_t)as * p.a_stage_bytes) + (uint32_t)(t.c0 + mt * 128) * Cfg::ROWB);
+                    umma_desc<KC>(s2u(a_buf + (size_t)as * p.a_stage_bytes) + (uint32_t)(c0u + mt * 128) * Cfg::ROWB);
+                int tr = 0, ts = 0;                              // tap (tr, ts) of the next MMA, walked without division
                 for (int t0 = 0; t0 < taps; t0 += Cfg::TPS) {
                     mb_wait(&b_full[bs], bph);
-                    if (active) {
-                        tc_fence_after();
-                        const uint64_t bd0 = umma_desc<KC>(s2u(b_buf + (size_t)bs * Cfg::B_STAGE));
+                    tc_fence_after();
+                    const uint64_t bd0 = umma_desc<KC>(s2u(b_buf + (size_t)bs * Cfg::B_STAGE));
+                    uint64_t ad[Cfg::TPS];
+                    bool live[Cfg::TPS];
 #pragma unroll
-                        for (int q = 0; q < Cfg::TPS; ++q) {
-                            const int tp = t0 + q;
-                            if (tp < taps) {
-                                const int tr = tp / k, ts = tp - tr * k;
-                                const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(tr * Wp + ts) * Cfg::ROWB) >> 4);
-                                const uint64_t bd = bd0 + (uint64_t)((q * Cfg::B_TAP) >> 4);
-#pragma unroll
-                                for (int kk = 0; kk < KC / 16; ++kk)
-                                    tc_mma(d, ad + 2 * kk, bd + 2 * kk, idesc, (c | tp | kk) != 0);
-                            }
+                    for (int q = 0; q < Cfg::TPS; ++q) {
+                        live[q] = t0 + q < taps;
+                        ad[q] = a_desc0 + (uint64_t)(((uint32_t)(tr * Wp + ts) * Cfg::ROWB) >> 4);
+                        if (++ts == k) {
+                            ts = 0;
+                            ++tr;
                         }
-                        tc_commit(&b_empty[bs]);
-                    } else {
-                        mb_arrive(&b_empty[bs]);
                     }
-                    if (++bs == Cfg::B_STAGES) {
+                    if (elect_one()) {
+                        if (active) {
+#pragma unroll
+                            for (int q = 0; q < Cfg::TPS; ++q)
+                                if (live[q]) {
+                                    const uint64_t bd = bd0 + (uint64_t)((q * Cfg::B_TAP) >> 4);
+#pragma unroll
+                                    for (int kk = 0; kk < KC / 16; ++kk)
+                                        tc_mma(d, ad[q] + 2 * kk, bd + 2 * kk, idesc, (uint32_t)(c | (t0 + q) | kk));
+                                }
+                            tc_commit(&b_empty[bs]);
+                        } else {
+                            mb_arrive(&b_empty[bs]);
+                        }
+                    }
+                    __syncwarp();
+                    if (++bs == BS) {
                         bs = 0;
                         bph ^= 1;
                     }
                 }
-                if (active) tc_commit(&a_empty[as]);
-                else mb_arrive(&a_empty[as]);
+                if (elect_one()) {
+                    if (active) tc_commit(&a_empty[as]);
+                    else mb_arrive(&a_empty[as]);
+                }
+                __syncwarp();
                 if (++as == Cfg::A_STAGES) {
                     as = 0;
                     aph ^= 1;
                 }
             }
-            if (active) tc_commit(&t_full[acc]);
-            else mb_arrive(&t_full[acc]);
-            if (mt == 0) G2T(3);
+            if (elect_one()) {
+                if (active) tc_commit(&t_full[acc]);
+                else mb_arrive(&t_full[acc]);
+            }
+            __syncwarp();
+            if (mt == 0 && lane == 0) G2T(3);
             ++tcount;
             if (++acc == 2) {
                 acc = 0;
                 acc_ph ^= 1;
             }
+            nx = fetch();            // published by the producer before the last weight stage of the tile just issued
         }
     } else {
         // ============================== epilogue (4 warps): TMEM -> registers -> global ==============================
@@ -479,22 +571,16 @@ gconv2_fwd_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
     }
-    if (threadIdx.x == 0) {
-        // the last CTA to finish re-arms the scheduler for the next launch on this stream
-        __threadfence();
-        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
-            p.sched[0] = 0;
-            p.sched[1] = 0;
-            __threadfence();
-        }
-    }
+#ifdef HDMOE_G2_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 148) g2_span[blockIdx.x * 2 + 1] = g2_gtime();
+#endif
 }
 
 template <int KC, int N>
 static int launch_gconv2(const CUtensorMap* ta, const CUtensorMap& tb, const GConv2Params& p, cudaStream_t st) {
     using Cfg = Conv2Cfg<KC, N>;
     auto kfn = gconv2_fwd_kernel<KC, N>;
-    const int smem = Cfg::A_STAGES * p.a_stage_bytes + Cfg::B_STAGES * Cfg::B_STAGE + 1024;
+    const int smem = Cfg::A_STAGES * p.a_stage_bytes + p.b_stages * Cfg::B_STAGE + 1024;
     HDMOE_CHECK_ARG(smem <= 227 * 1024, "gconv2: tile does not fit shared memory (%d bytes)", smem);
     HDMOE_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
@@ -509,6 +595,9 @@ using namespace hdmoe;
 #ifdef HDMOE_G2_TRACE
 extern "C" int hdmoe_g2_trace_read(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, g2_trace, sizeof(long long) * 148 * 64);
+}
+extern "C" int hdmoe_g2_span_read(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g2_span, sizeof(long long) * 148 * 2);
 }
 #endif
 
@@ -561,7 +650,9 @@ extern "C" int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_
     }
     int smax = 0, box_bytes_max = 0;
     int cls_box_rows[kG2Classes];
-    const int b_ring_bytes = 4 * (Cout <= 64 ? 2 : 1) * Cout * KC * 2;      // Conv2Cfg: B_STAGES * B_STAGE
+    const int tps = g2_tps(KC, Cout);
+    const int b_stage_bytes = tps * Cout * KC * 2;                            // Conv2Cfg::B_STAGE
+    const int b_ring_bytes = Conv2Cfg<32, 32>::B_STAGES_MIN * b_stage_bytes;  // the minimum ring decides the tile size
     // M-tiles per tile: as many as there are issuer warps, fewer only if two halo buffers would not fit shared memory
     for (int mt_try = mt_max; mt_try >= 1; --mt_try) {
         smax = 0;
@@ -598,6 +689,8 @@ extern "C" int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_
     p.smax = smax;
     p.n_tiles = cap_rows * smax;
     p.a_stage_bytes = ((box_bytes_max + 1023) / 1024) * 1024;
+    p.b_stages = g2_b_stages(b_stage_bytes);          // deeper ring where the halo buffers leave room
+    while (p.b_stages > 4 && 2 * p.a_stage_bytes + p.b_stages * b_stage_bytes + 1024 > 227 * 1024) --p.b_stages;
     cudaStream_t st = (cudaStream_t)stream;
     p.sched = sched_slot(st);
     HDMOE_CHECK_ARG(p.sched != nullptr, "gconv2_fwd: more than %d distinct streams in use", kSchedSlots);
@@ -621,7 +714,7 @@ extern "C" int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_
     {
         cuuint64_t dims[2] = {(cuuint64_t)Cin_pad, (cuuint64_t)w_rows_total};
         cuuint64_t strides[1] = {(cuuint64_t)Cin_pad * 2};
-        cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(Cout <= 64 ? 2 * Cout : Cout)};
+        cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(tps * Cout)};
         cuuint32_t es[2] = {1, 1};
         CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(Wt), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -22,6 +22,8 @@
 // Everything else follows v1: flattened halo formulation (A = dY strip box with zero-filled surplus columns, B = the
 // zero-padded input window, tap (r, s) reads it at start + (r * Wp + s) rows), item = (row chunk, tap group), split-K
 // over row chunks with `red.global.add.v4.f32`, dynamic item scheduler (last rows first), 4 MMA-issuer warps.
+#include <type_traits>
+
 #include "tc.cuh"
 #include "../../include/hdmoe_gemm.h"
 
@@ -134,13 +136,15 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
 
     // Walk of one item, identical in every role.  Calls stage_fn for every pipeline stage and flush_fn whenever the
     // accumulators must be written out.  Returns the number of flushes (= accumulator buffers consumed).
-    auto walk = [&](int item, auto&& stage_fn, auto&& flush_fn) {
+    // `converged` (a whole warp walks together): the expert ids are made warp-uniform with redux so that everything
+    // derived from them stays on the uniform datapath (see the issuer role).
+    auto walk = [&](int item, auto converged, auto&& stage_fn, auto&& flush_fn) {
         const int g = item % p.gmax, rc = p.n_items / p.gmax - 1 - item / p.gmax;       // last row chunks first
         const int r0 = rc * p.rows_per_item, r1 = min(r0 + p.rows_per_item, n_rows);
         int cur_e = -1, cur_kc = 0;
         bool fresh = true;
         for (int r = r0; r < r1; ++r) {
-            const int e = p.row_expert[r];
+            const int e = decltype(converged)::value ? uni(p.row_expert[r]) : p.row_expert[r];
             if (e < 0 || e >= p.n_experts) continue;
             const int kc = p.kclass[e];
             if (g >= p.ngroups[kc]) continue;
@@ -191,7 +195,7 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                     qph ^= 1;
                 }
                 if (item < 0) break;
-                walk(item,
+                walk(item, std::false_type{},
                      [&](int r, int e, int kc, int g, int st, int c, bool) {
                          const int pad = (p.ksize[kc] - 1) >> 1;
                          mb_wait(&empty[s], ph ^ 1);
@@ -209,24 +213,26 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         }
     } else if (warp <= kW2Issuers) {
         // ============================== MMA issuers (units of the group dealt round-robin) ==============================
-        if (lane == 0) {
+        // The whole warp walks the item converged and one elected lane issues (descriptors and barrier addresses in
+        // uniform registers; a single-lane loop costs an ELECT + R2UR waterfall per UTCHMMA, see gconv2.cu).
+        {
             // D[128 x KC] (+)= A^T B : A, B MN-major (bits 15, 16), M = 128, N = KC, bf16 -> fp32
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                        ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const int me = warp - 1;
+            const int me = uni(warp) - 1;
             int s = 0, buf = 0;
             uint32_t ph = 0, tph[2] = {0, 0};
             bool need_buf = true;                       // the next stage is the first of a fresh accumulator buffer
             WGT_DECL;
             for (;;) {
-                const int item = next_item(false);
+                const int item = uni(next_item(true));
                 WGT_LAP(0);                             // waiting for an item
                 if (item < 0) break;
                 WGT_CNT(5);
-                walk(item,
+                walk(item, std::true_type{},
                      [&](int r, int e, int kc, int g, int st, int c, bool first) {
-                         const int Wp = p.wp[kc], upr = p.upr[kc];
-                         const int u_lo = g * p.upg, u_hi = min(p.nunits[kc], u_lo + p.upg);
+                         const int Wp = uni(p.wp[kc]), upr = uni(p.upr[kc]);
+                         const int u_lo = g * p.upg, u_hi = min(uni(p.nunits[kc]), u_lo + p.upg);
                          const int nslice = (p.SH * Wp) >> 4;
                          WGT_LAP(1);                             // walk / decode
                          if (need_buf) {
@@ -242,15 +248,20 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                          const uint32_t b0 = s2u(smem + (size_t)s * stage_bytes) + p.a_stage_bytes;
                          const uint64_t ad0 = umma_desc_mn2<ROWA>(a0, ROWA);     // atoms one position row apart
                          const uint64_t bd0 = umma_desc_mn2<ROWB_>(b0, 0);
+                         const bool leader = elect_one();
                          for (int u = u_lo + me; u < u_hi; u += kW2Issuers) {
                              const int tr = u / upr, s0 = (u - tr * upr) * TPM;
                              const uint32_t d = tmem_base + (uint32_t)(buf * kW2BufCols + ((u - u_lo) * p.nchunks + c) * KC);
                              const uint64_t bd = bd0 + (uint64_t)(((uint32_t)(tr * Wp + s0) * ROWB_) >> 4);
-                             for (int j = 0; j < nslice; ++j)
-                                 tc_mma(d, ad0 + (uint64_t)((j * 16 * ROWA) >> 4), bd + (uint64_t)((j * 16 * ROWB_) >> 4), idesc,
-                                        !(first && j == 0));
+                             if (leader) {
+#pragma unroll 4
+                                 for (int j = 0; j < nslice; ++j)
+                                     tc_mma(d, ad0 + (uint64_t)((j * 16 * ROWA) >> 4), bd + (uint64_t)((j * 16 * ROWB_) >> 4),
+                                            idesc, !(first && j == 0));
+                             }
                          }
-                         tc_commit(&empty[s]);
+                         if (leader) tc_commit(&empty[s]);
+                         __syncwarp();
                          WGT_LAP(3);                             // issuing MMAs
                          if (++s == kW2Stages) {
                              s = 0;
@@ -259,13 +270,14 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                      },
                      [&](int, int, int) {
                          WGT_CNT(6);
-                         tc_commit(&t_full[buf]);           // all accumulators of the group are final
+                         if (elect_one()) tc_commit(&t_full[buf]);           // all accumulators of the group are final
+                         __syncwarp();
                          tph[buf] ^= 1;
                          buf ^= 1;
                          need_buf = true;
                      });
             }
-            if (me == 0) WGT_OUT(0);
+            if (me == 0 && lane == 0) WGT_OUT(0);
         }
     } else {
         // ============================== epilogue: TMEM -> vector atomics ==============================
@@ -277,7 +289,7 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         for (;;) {
             const int item = next_item(true);
             if (item < 0) break;
-            walk(item, [&](int, int, int, int, int, int, bool) {},
+            walk(item, std::false_type{}, [&](int, int, int, int, int, int, bool) {},
                  [&](int e, int kc, int g) {
                      const int k = p.ksize[kc], upr = p.upr[kc];
                      const int u_lo = g * p.upg, u_hi = min(p.nunits[kc], u_lo + p.upg);

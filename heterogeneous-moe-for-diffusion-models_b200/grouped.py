@@ -81,6 +81,9 @@ class _GConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        # The `token` input only orders the backward pass: its edge makes the W-PREP backward node wait for this node
+        # (autograd counts dependencies on edges, whatever flows through them), so its gradient is None -- a zeros tensor
+        # per convolution cost 44 fill + 38 accumulate launches per step inside the expert backward.
         (x,) = ctx.saved_tensors
         runner, layer = ctx.runner, ctx.runner.layers[ctx.li]
         runner.check_generation(ctx.gen)
@@ -93,7 +96,7 @@ class _GConvFn(torch.autograd.Function):
             if layer.cin_rows < layer.cin_pad:
                 dx = F.pad(dx, (0, layer.cin_pad - layer.cin_rows))
         runner.weight_grad_async(layer, x, dy, plan)
-        return dx, torch.zeros_like(ctx.runner.token_like), None, None
+        return dx, None, None, None
 
 
 class _PrepWeights(torch.autograd.Function):
@@ -165,7 +168,6 @@ class GroupedUnetExperts:
         self._built_for = None
         self._wg_stream, self._wg_pending = None, False
         self.plan = None
-        self.token_like = None
         # The operand buffers, the weight-gradient accumulator and the W-PREP tables are persistent (pointer-stable for
         # CUDA-graph replay) and therefore hold the state of ONE forward: `generation` counts forwards that took the
         # autograd path, and every backward node checks that it belongs to the latest one.
@@ -371,7 +373,6 @@ class GroupedUnetExperts:
         if self._built_for != dev:
             self._build(dev)
         self.plan = plan
-        self.token_like = torch.zeros(1, device=dev)
         # autograd path whenever a gradient can flow (independent of .training: eval-mode forwards under autograd
         # propagate to the input and the expert parameters like the reference); `training` only selects the forced
         # weight normalisation (Q6) and dropout

@@ -70,7 +70,6 @@ class GroupedRouterTrunk:
         self._plans = {}
         self._wg_stream, self._wg_pending = None, False
         self.plan = None
-        self.token_like = None
         self.generation = 0
 
     @staticmethod
@@ -201,7 +200,6 @@ class GroupedRouterTrunk:
         if key not in self._plans:
             self._plans[key] = _TrunkPlan(self.E, B, dev)
         plan = self.plan = self._plans[key]
-        self.token_like = torch.zeros(1, device=dev)
         need_grad = torch.is_grad_enabled() and (any(x.requires_grad for x in xs)
                                                  or any(p_.requires_grad for p_ in self._params()))
         if need_grad:

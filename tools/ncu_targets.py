@@ -91,7 +91,56 @@ def vit_case():
         D.router_to_unet_experts(x, ex, wr, t, tx, top_k=1).backward(gy)
     return run
 
-cases = [gconv_case(), attn_case(), gn_case(), dispatch_case(), router_case(), glue_case(), vit_case()]
+def trunk_case():
+    """router trunks of both routers on the tcgen05 kernels (dense N = 64 / 128 layers) + bf16 GroupNorm kernels"""
+    from hdmoe_b200 import model_components as mc
+    from hdmoe_b200.router_trunk import GroupedRouterTrunk
+    rs = [mc.Router(in_channels=32, time_dim=64, top_k=1, num_experts=4).to(dev).train() for _ in range(2)]
+    runner = GroupedRouterTrunk(rs)
+    feats = torch.randn(256, 32, 32, 32, device=dev, requires_grad=True)
+    scaling = torch.rand(256, 2, device=dev) + 0.5
+    gp = torch.randn(256, 128, device=dev)
+    def run():
+        a, b, t = ops.scale_pair(feats, scaling, want_trunk=True)
+        pv, pu = runner(None, True, pre_nhwc=t)
+        ((pv * gp).sum() + (pu * gp).sum() + a.sum() + b.sum()).backward()
+    return run
+
+def tail_case():
+    """channels-last HDMOEM tail: cfg1 swap + text-blend / gate / mix kernels, loss data term, fused optimizer"""
+    from hdmoe_b200.optim import FusedAdamW
+    B, S, C = 256, 1024, 32
+    u, v, a, b = (torch.randn(B, S, C, device=dev, requires_grad=True) for _ in range(4))
+    w = torch.rand(B, device=dev, requires_grad=True)
+    alpha = torch.tensor(0.3, device=dev, requires_grad=True)
+    W1 = (torch.randn(32, 64, 1, 1, device=dev) / 8).requires_grad_(True)
+    W2 = (torch.randn(2, 32, 1, 1, device=dev) / 6).requires_grad_(True)
+    d, x0 = torch.randn(B, 4, 32, 32, device=dev, requires_grad=True), torch.randn(B, 4, 32, 32, device=dev)
+    params = [torch.nn.Parameter(torch.randn(n, device=dev)) for n in (2_000_000, 3_000_000, 4_000_000, 38_821)]
+    opt = FusedAdamW(params, lr=5e-4, max_grad_norm=1.0)
+    for p_ in params:
+        p_.grad = torch.randn_like(p_)
+    def run():
+        q, c = ops.trunk_swap(u, v, w)
+        mix, g = ops.trunk_gate(q, a, b, alpha, W1, W2, 32, 32)
+        (mix.sum() + c.sum() + ops.sqerr_rows(d, x0).sum()).backward()
+        opt.step()
+    return run
+
+def plan_case():
+    T, E, K = 1048576, 64, 1
+    idx = torch.randint(0, E, (T, K), device=dev, dtype=torch.int32)
+    tw = torch.ones(T, K, device=dev)
+    x = torch.randn(T, 128, device=dev).to(torch.bfloat16)
+    sp = torch.zeros(T, E, device=dev).scatter_(1, idx.long(), 1.0)
+    def run():
+        plan = ops.dispatch_plan_from_topk(idx, tw, E)
+        rows = ops.permute(plan, x)
+        ops.combine(rows[0], sp, plan)
+    return run
+
+cases = [gconv_case(), attn_case(), gn_case(), dispatch_case(), router_case(), glue_case(), vit_case(), trunk_case(),
+         tail_case(), plan_case()]
 for c in cases:
     c(); c()
 torch.cuda.synchronize()

@@ -51,3 +51,17 @@ for b in (0, 73, 147):
     print(f"CTA {b}: {cyc} cycles in {ns} ns -> {cyc / ns:.3f} GHz; start offset {(a[b, 0, 6] - g_start) / 1e3:.1f} us, end offset {(a[b, last, 7] - g_start) / 1e3:.1f} us")
 ends_ns = sorted((max(a[b, t, 7] for t in range(8)) - g_start) / 1e3 for b in range(148))
 print("CTA end times (us): min %.1f median %.1f max %.1f" % (ends_ns[0], ends_ns[74], ends_ns[-1]))
+
+if VER == "2" and hasattr(lib, "hdmoe_g2_span_read"):
+    sp = (C.c_longlong * (148 * 2))()
+    lib.hdmoe_g2_span_read.argtypes = [C.c_void_p]
+    lib.hdmoe_g2_span_read(sp)
+    sp = np.array(sp[:], dtype=np.int64).reshape(148, 2)
+    k0, k1 = sp[:, 0].min(), sp[:, 1].max()
+    first_tile = np.array([a[b, 0, 6] for b in range(148)])
+    last_epi = np.array([max(a[b, t, 7] for t in range(8)) for b in range(148)])
+    print("kernel span by globaltimer (first CTA entry -> last CTA exit): %.1f us" % ((k1 - k0) / 1e3))
+    print("CTA entry spread: %.2f us; entry -> first tile start (prologue): median %.2f us max %.2f us" % (
+        (sp[:, 0].max() - k0) / 1e3, np.median(first_tile - sp[:, 0]) / 1e3, (first_tile - sp[:, 0]).max() / 1e3))
+    print("last traced epilogue end -> CTA exit (teardown): median %.2f us; CTA exit spread: min %.1f median %.1f max %.1f us" % (
+        np.median(sp[:, 1] - last_epi) / 1e3, (sp[:, 1].min() - k0) / 1e3, np.median(sp[:, 1] - k0) / 1e3, (k1 - k0) / 1e3))
