@@ -22,7 +22,6 @@ $(LIB): $(OBJ)
 TRACEFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -Iinclude -shared
 trace:
 	$(NVCC) $(TRACEFLAGS) -DHDMOE_G2_TRACE -o tools/libg2trace.so $(PKG)/csrc/gconv2.cu $(PKG)/csrc/core.cu -lcudart
-	$(NVCC) $(TRACEFLAGS) -DHDMOE_G3_TRACE -o tools/libg3trace.so $(PKG)/csrc/gconv3.cu $(PKG)/csrc/core.cu -lcudart
 	$(NVCC) $(TRACEFLAGS) -DHDMOE_WG_TRACE -o tools/libwg2trace.so $(PKG)/csrc/gwgrad2.cu $(PKG)/csrc/core.cu -lcudart
 probes:
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_rate tools/umma_rate.cu

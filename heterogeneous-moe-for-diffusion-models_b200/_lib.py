@@ -57,7 +57,6 @@ PROTOTYPES = {
     "hdmoe_edm_heun_correct": (_i, [_p, _p, _p, _i, _p, _p, _i, _f, _f, _f, _f, _p, _p, _i64, _p]),
     "hdmoe_wprep_fwd": (_i, [_p, _p, _i, _i, _p]),
     "hdmoe_gconv2_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
-    "hdmoe_gconv3_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _f, _f, _p]),
     "hdmoe_gconv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _p, _p, _i, _p, _p, _p]),
     "hdmoe_nhwc_pixnorm_silu_fwd": (_i, [_p, _p, _p, _i64, _i, _p]),
     "hdmoe_nhwc_pixnorm_silu_bwd": (_i, [_p, _p, _p, _p, _i64, _i, _p]),

@@ -564,30 +564,22 @@ def gconv_raw(x, w_cat, cout: int, w_rows_total: int, row_expert, n_rows_dev, ks
         scale = _f32c(scale)
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == y.shape
-    fn = L.lib().hdmoe_gconv3_fwd if (_GCONV_IMPL[0] == 3 and cout in (32, 64)) else L.lib().hdmoe_gconv2_fwd
+    fn = L.lib().hdmoe_gconv2_fwd
     L.check(fn(_p(x), _p(w_cat), _p(y), cap, H, W, cin_pad, cout, w_rows_total, _p(row_expert), _p(n_rows_dev), E, ks, wr,
                _p(scale), int(act), _p(residual), float(res_a), float(res_b), _st()), "gconv_fwd")
     return y
 
 
-# 2 = halo-reuse kernel (gconv2.cu, default); 3 = tap-group kernel (gconv3.cu: Cout 32 / 64, other widths use 2).
-# Which one is the default is decided per measured shape table (profiles/); 3 needs experimental=True until then.
-_GCONV_IMPL = [2]
-
-
+# The grouped convolution has ONE product implementation (gconv2.cu: halo reuse).  The tap-group variant gconv3 passed
+# the parity tests on B200 in round 2 and lost on every layer shape (profiles/r2_gconv3_vs_gconv2.md); it is archived in
+# tools/legacy/.  set_gconv_impl / get_gconv_impl stay for callers that pinned the default.
 def set_gconv_impl(v: int, experimental: bool = False) -> None:
-    if v not in (2, 3):
-        raise ValueError("gconv implementation must be 2 or 3")
-    if v == 3 and not experimental and not _GCONV3_VALIDATED:
-        raise RuntimeError("gconv3 is experimental: pass experimental=True")
-    _GCONV_IMPL[0] = v
+    if v != 2:
+        raise ValueError("gconv implementation 2 (halo reuse) is the only one in the library; see tools/legacy/")
 
 
 def get_gconv_impl() -> int:
-    return _GCONV_IMPL[0]
-
-
-_GCONV3_VALIDATED = True       # passes tests/test_gpu_gconv.py on B200 (round 2); not the default: see profiles/r2_gconv_shapes.md
+    return 2
 
 
 def gconv_wgrad_raw(x, dy, dw, row_expert, n_rows_dev, ksizes, wrows):

@@ -32,16 +32,6 @@ int hdmoe_gconv2_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H
                      const int32_t* ksize_host, const int32_t* wrow_host, const float* scale, int act,
                      const void* residual, float res_a, float res_b, void* stream);
 
-/* EXPERIMENTAL third implementation of the same contract (opt-in: ops.set_gconv_impl(3); the product path uses
- * hdmoe_gconv2_fwd): tap groups stacked in the MMA's N dimension (one M128 x N128 MMA per 128 / Cout taps of a kernel
- * row), shift-add in the epilogue.  Cout in {32, 64} only.  The formulation is validated on hardware by
- * tools/umma_tpair_probe.cu; this kernel itself has not run on a GPU yet (written at the end of round 1 without GPU
- * budget) and must pass tools/dbg_gconv.py v3 before it is made the default. */
-int hdmoe_gconv3_fwd(const void* X, const void* Wt, void* Y, int cap_rows, int H, int W, int Cin_pad, int Cout,
-                     int64_t w_rows_total, const int32_t* row_expert, const int32_t* n_rows_dev, int n_experts,
-                     const int32_t* ksize_host, const int32_t* wrow_host, const float* scale, int act,
-                     const void* residual, float res_a, float res_b, void* stream);
-
 /* Grouped convolution weight gradient (tcgen05, MN-major operands, split-K with vector atomics):
  *   dW[wrow[e] + tap*Cout + o, c] += sum over rows r of expert e and pixels q of dY[r,q,o] * Xpad[r, q+delta_tap, c]
  * dW is fp32 [w_rows_total, Cin_pad] in the tap-major block layout of the forward operand and must be zeroed by

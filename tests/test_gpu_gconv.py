@@ -2,7 +2,7 @@
 ops.gconv_wgrad_raw), against the oracle's MP_Conv arithmetic (oracle.mp_weight + the asymmetric 'same' pad +
 conv2d of oracle.mp_conv, models/model_internals.py:253-271) evaluated in float64 on the same bf16-rounded operands.
 
-  forward / data gradient (gconv2, and gconv3 where it applies): rel-L2 <= 4e-3  (one bf16 rounding of the output)
+  forward / data gradient (gconv2): rel-L2 <= 4e-3  (one bf16 rounding of the output)
   weight gradient (gwgrad2, fp32 accumulators):                    rel-L2 <= 1e-3
   W-PREP operand (bf16, tap-major) vs bf16(oracle.mp_weight):      <= 1 bf16 ulp per element
 
@@ -142,21 +142,10 @@ def _ids(s):
     return f"R{s[0]}_{s[1]}x{s[2]}_ci{s[3]}_co{s[4]}_k{''.join(map(str, s[5]))}"
 
 
-@pytest.fixture(params=[2, 3], ids=["gconv2", "gconv3"])
-def impl(request):
-    from hdmoe_b200 import ops
-    old = ops.get_gconv_impl()
-    ops.set_gconv_impl(request.param, experimental=True)
-    yield request.param
-    ops.set_gconv_impl(old, experimental=True)
-
-
 @pytest.mark.parametrize("shape", SHAPES, ids=_ids)
-def test_gconv_forward_vs_oracle(shape, impl):
+def test_gconv_forward_vs_oracle(shape):
     from hdmoe_b200 import ops
     R, H, W, cin, cout, ks, counts = shape
-    if impl == 3 and cout not in (32, 64):
-        pytest.skip("gconv3 covers Cout 32 / 64")
     c = _Case(*shape)
     c.operand_matches_oracle()
     y = ops.gconv_raw(c.x_nhwc, c.w_fwd, cout, c.rows_total, c.row_e, c.n_rows_dev, ks, c.wrow)
@@ -176,7 +165,7 @@ def test_gconv_forward_vs_oracle(shape, impl):
                          ids=["scale_silu", "residual", "scale_silu_residual", "scale"])
 @pytest.mark.parametrize("shape", [(4, 32, 32, 64, 64, [3, 5], [2, 2]), (6, 32, 32, 32, 32, [3, 3, 5, 5], [1, 2, 0, 2]),
                                    (9, 16, 16, 64, 64, [3, 5], [4, 5])], ids=_ids)
-def test_gconv_fused_epilogue_vs_oracle(shape, flags, impl):
+def test_gconv_fused_epilogue_vs_oracle(shape, flags):
     """out = res_a * residual + res_b * mp_silu(scale * conv): the eval-mode fusion of Unet_block
     (models/model_components.py:240-253)."""
     from hdmoe_b200 import ops
@@ -197,14 +186,12 @@ def test_gconv_fused_epilogue_vs_oracle(shape, flags, impl):
 
 
 @pytest.mark.parametrize("shape", [s for s in SHAPES if s[3] >= 32], ids=_ids)
-def test_gconv_data_gradient_vs_oracle(shape, impl):
+def test_gconv_data_gradient_vs_oracle(shape):
     """dX = conv_transpose(dY, W_hat) through the same kernel with the transposed, tap-flipped operand W-PREP writes
     (HDMOE_WLAYOUT_TAPS_T), against torch.nn.grad.conv2d_input in float64."""
     from hdmoe_b200 import ops
     R, H, W, cin, cout, ks, counts = shape
     c = _Case(*shape, seed=9)
-    if impl == 3 and c.cin_rows not in (32, 64):
-        pytest.skip("gconv3 covers output widths 32 / 64")
     if cout % 32 != 0:
         pytest.skip("data-gradient K must be a multiple of 32")
     dy = torch.randn(R, H, W, cout, generator=c.gen).to(torch.bfloat16)

@@ -6,7 +6,7 @@ sys.path.insert(0, '.')
 import hdmoe_b200
 from hdmoe_b200 import _lib as L
 lib = L.lib()
-FN = {'v2': lib.hdmoe_gconv2_fwd, 'v3': lib.hdmoe_gconv3_fwd}.get(sys.argv[1] if len(sys.argv) > 1 else '', lib.hdmoe_gconv2_fwd)
+FN = lib.hdmoe_gconv2_fwd
 dev = "cuda"
 counts = [36, 48, 75, 97]
 ks = [3, 3, 5, 5]

@@ -1,5 +1,5 @@
 """Per-shape table of the grouped convolution kernels (forward, data gradient, weight gradient) over every U-Net expert
-layer of SURVEY Appendix D at the bench routing: python tools/perf_shapes.py [2|3] [--no-cudnn] -> JSON on stdout."""
+layer of SURVEY Appendix D at the bench routing: python tools/perf_shapes.py [--no-cudnn] -> JSON on stdout."""
 import json
 import sys
 import torch
@@ -8,8 +8,7 @@ import bench
 import hdmoe_b200  # noqa: F401
 from hdmoe_b200 import ops
 
-impl = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2
-ops.set_gconv_impl(impl, experimental=True)
+impl = 2
 dev = torch.device("cuda", 0)
 peaks = bench.load_peaks()
 flush = bench.L2Flusher(dev)

@@ -1,6 +1,6 @@
 import ctypes as C, sys, torch, numpy as np
 import os
-VER = os.environ.get("GVER", "2")
+VER = "2"
 lib = C.CDLL(os.environ.get("G2LIB", "tools/libg%strace.so" % VER))
 dev = "cuda"
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 16
