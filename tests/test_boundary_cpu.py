@@ -186,3 +186,43 @@ def test_fused_vit_weight_layout_matches_kernel_order():
                 assert meta.w_off[b][e] - meta.w_off[b - 1][e] == vit_fused._WBLOCK
     # the CPU never takes the fused path (no CPU fallback of the kernels; the composite torch path runs instead)
     assert not vit_fused.fusable(experts, torch.zeros(2, 32, 32, 32))
+
+
+def test_checkpoint_file_format_round_trip_and_reference_load(tmp_path):
+    """save_checkpoint writes the reference's dictionary (Utils/training.py:242-271): it reloads here (model + AdamW
+    moments) and, where the unmodified reference is importable (the build container), into the reference's own model
+    with strict key checking, as Utils/training.py:301-304 does."""
+    import sys
+    from hdmoe_b200.training import checkpoint_dir, load_checkpoint, save_checkpoint
+    torch.manual_seed(0)
+    model = c2.preconditioned_HDMOEM(**TINY)
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4)
+    for p in model.parameters():
+        p.grad = torch.randn_like(p) * 1e-2
+    opt.step()
+    cfg = {"model_configs": {"save_dir": str(tmp_path / "ck")}, "note": "unit test"}
+    assert checkpoint_dir(cfg) == str(tmp_path / "ck") and checkpoint_dir({}) == "./checkpoints"
+    path = save_checkpoint(model, opt, step=7, mse_score=0.25, configs=cfg, filename="m.pt")
+    raw = torch.load(path, weights_only=False)
+    assert sorted(raw) == ["config", "model_state_dict", "mse", "optimizer_state_dict", "step"]
+    torch.manual_seed(1)
+    model2 = c2.preconditioned_HDMOEM(**TINY)
+    opt2 = torch.optim.AdamW(model2.parameters(), lr=1e-3)
+    meta = load_checkpoint(path, model2, opt2)
+    assert meta["step"] == 7 and meta["mse"] == 0.25 and meta["config"]["note"] == "unit test"
+    for (k, a), b in zip(model.state_dict().items(), model2.state_dict().values()):
+        assert torch.equal(a, b), k
+    s1, s2 = opt.state_dict()["state"], opt2.state_dict()["state"]
+    assert s1.keys() == s2.keys() and all(torch.equal(s1[i]["exp_avg_sq"], s2[i]["exp_avg_sq"]) for i in s1)
+    assert opt2.param_groups[0]["lr"] == 5e-4
+    if not os.path.isdir("/root/reference/models"):
+        return
+    sys.path.insert(0, "/root/reference")
+    try:
+        from models.model_config2 import preconditioned_HDMOEM as RefModel
+    finally:
+        sys.path.remove("/root/reference")
+    ref = RefModel(**TINY)
+    ref.load_state_dict(raw["model_state_dict"])           # strict: every key and shape is the reference's
+    torch.save({"model_state_dict": ref.state_dict()}, tmp_path / "ref.pt")
+    model2.load_state_dict(torch.load(tmp_path / "ref.pt")["model_state_dict"])
