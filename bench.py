@@ -673,6 +673,53 @@ def sampler_throughput(device, rank, world, total_batch=1024, steps=18, guidance
             "execution": "one CUDA graph per denoiser evaluation, fused Heun kernels between; ranks sample independently"}
 
 
+def ep_exchange_breakdown(rank, world, device, B=64, res=64, top_k=1, iters=10):
+    """What the expert-parallel layer puts on NVLink per train step at config C, timed alone: the equal-split
+    all-to-alls of the image / time / text send buffers (dispatch), the image-row all-to-all back (combine) and their
+    backward mirrors, at the layer's static buffer sizes (G segments of C = T*k rows, bf16).  Device time, max over
+    ranks.  Bytes: `wire` = rows that actually leave the GPU for a balanced router ((G-1)/G of T*k rows), `buffer` =
+    what the fixed-capacity exchange moves (every segment, live or zero-filled)."""
+    import torch.distributed as dist
+    C = B * top_k
+    widths = {"image": 32 * res * res, "time": 64, "text": 768}
+    bufs = {k: torch.randn(world * C, w, device=device).to(torch.bfloat16) for k, w in widths.items()}
+    outs = {k: torch.empty_like(v) for k, v in bufs.items()}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        barrier(world)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return max_over_ranks(a.elapsed_time(b), world, device) / iters * 1e3
+
+    def dispatch():
+        for k in widths:
+            dist.all_to_all_single(outs[k], bufs[k])
+
+    def combine():
+        dist.all_to_all_single(outs["image"], bufs["image"])
+
+    us_d, us_c = timed(dispatch), timed(combine)
+    cnt = torch.zeros(world * 4, dtype=torch.int64, device=device)
+    us_counts = timed(lambda: dist.all_gather_into_tensor(cnt, cnt[:4].contiguous()))
+    row = sum(widths.values()) * 2
+    buf_bytes = world * C * (row + widths["image"] * 2) * 2            # dispatch + combine, forward + backward
+    wire_bytes = int(C * (world - 1) / world * (row + widths["image"] * 2) * 2)
+    per_step_us = 2 * (us_d + us_c) + us_counts
+    return {"dispatch_a2a_us": round(us_d, 1), "combine_a2a_us": round(us_c, 1), "counts_allgather_us": round(us_counts, 1),
+            "exchange_us_per_step": round(per_step_us, 1), "buffer_bytes_per_step": buf_bytes,
+            "wire_bytes_per_step_balanced": wire_bytes,
+            "buffer_GBs": round(buf_bytes / per_step_us / 1e3, 1),
+            "note": "one expert-parallel MoE layer (U-Net experts) per step: forward dispatch + combine and their "
+                    "backward mirrors, NCCL all_to_all_single timed alone (no overlap), bf16 payload"}
+
+
 def config_c_throughput(args, rank, world, device, parallelism, B=64, steps=5):
     """BASELINE configs[2]: model_config2 at 4x64x64 (11.2 M parameters), bf16 expert path, batch 64 per GPU, whole train
     step; "dp" = data-parallel replicas, "ep" = U-Net experts sharded over the ranks (static-shape all-to-all layer)."""
@@ -711,8 +758,21 @@ def scale_extras(args, rank, world, device):
     cfg_c = {"dp": config_c_throughput(args, rank, world, device, "dp")}
     if world > 1:
         cfg_c["ep"] = config_c_throughput(args, rank, world, device, "ep")
+        # the expert-parallel step runs eagerly (make_runner): the like-for-like bar is the data-parallel step run eagerly
+        # too; the difference between the two eager steps is what expert parallelism itself costs, and the exchange
+        # timed alone says how much of that is NVLink time
+        import copy
+        eager_args = copy.copy(args)
+        eager_args.no_graph = True
+        cfg_c["dp_eager"] = config_c_throughput(eager_args, rank, world, device, "dp")
+        try:
+            cfg_c["exchange"] = ep_exchange_breakdown(rank, world, device)
+        except Exception as exc:                      # noqa: BLE001
+            cfg_c["exchange"] = {"error": str(exc)[:200]}
         try:
             cfg_c["ep_over_dp"] = round(cfg_c["ep"]["value"] / cfg_c["dp"]["value"], 3)
+            cfg_c["ep_over_dp_eager"] = round(cfg_c["ep"]["value"] / cfg_c["dp_eager"]["value"], 3)
+            cfg_c["ep_extra_ms_vs_dp_eager"] = round(cfg_c["ep"]["ms_per_step"] - cfg_c["dp_eager"]["ms_per_step"], 2)
         except (KeyError, ZeroDivisionError):
             pass
     cfg_c.update({k: cfg_c["dp"].get(k) for k in ("metric", "value", "unit", "ms_per_step", "workload")})

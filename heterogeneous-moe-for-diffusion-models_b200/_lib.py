@@ -34,6 +34,14 @@ class OptTensorDesc(C.Structure):
                 ("chunk_start", C.c_int32), ("pad", C.c_int32)]
 
 
+MAX_MASK_EXPERTS = 16
+
+
+class MaskGenDesc(C.Structure):       # hdmoe_maskgen_t
+    _fields_ = [("centers", _f * MAX_MASK_EXPERTS), ("p_mean", _f), ("p_std", _f), ("bandwidth", _f),
+                ("n_experts", C.c_int32), ("min_active", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/hdmoe_b200.h one to one
 PROTOTYPES = {
     "hdmoe_version": (_i, []),
@@ -94,6 +102,7 @@ PROTOTYPES = {
     "hdmoe_scaling_router_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "hdmoe_sqerr_rows": (_i, [_p, _p, _p, _i, _i64, _p]),
     "hdmoe_sqerr_rows_bwd": (_i, [_p, _p, _p, _p, _i, _i64, _p]),
+    "hdmoe_train_inputs": (_i, [_p, _p, _p, _p, _i, _i64, C.POINTER(MaskGenDesc), _p, C.POINTER(MaskGenDesc), _p, _p]),
     "hdmoe_optim_chunk_elems": (_i, []),
     "hdmoe_adamw_step": (_i, [_p, _i, _i, _p, _p, _p, _f, _f, _f, _f, _i, _p]),
 }

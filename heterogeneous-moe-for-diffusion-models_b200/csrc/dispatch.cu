@@ -807,11 +807,8 @@ extern "C" int hdmoe_permute_rows(const void* const* srcs, void* const* dsts, co
         }
         const long long total = (long long)cap * base;
         const int smem = kBulkStages * kChunk;
-        static bool attr_set = false;
-        if (!attr_set) {
-            HDMOE_CHECK_CUDA(cudaFuncSetAttribute(permute_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
-        }
+        // per (device, function) attribute: set on every call (cheap), a process may drive several GPUs
+        HDMOE_CHECK_CUDA(cudaFuncSetAttribute(permute_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         long long g = total < (long long)kNumSMs * 2 ? total : (long long)kNumSMs * 2;
         permute_bulk_kernel<<<(int)g, 32, smem, st>>>(a, row_src, n_rows_dev, cap, base);
         HDMOE_CHECK_LAUNCH();

@@ -346,3 +346,93 @@ extern "C" int hdmoe_sqerr_rows_bwd(const float* d, const float* x, const float*
     HDMOE_CHECK_LAUNCH();
     return HDMOE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// On-device producers of the train step's inputs: the noise add of Utils/training.py:133-134
+// (noise = eps * sigma; x = latent + noise, fp32, two roundings as in the reference) and BOTH MaskGenerator band masks
+// (Utils/utils.py:281-309) in one launch: ~25 small launches and no host round trip per step.
+// ---------------------------------------------------------------------------------------------------------------
+namespace hdmoe {
+struct MaskGenParams {
+    float centers[HDMOE_MAX_MASK_EXPERTS];
+    float p_mean, div, bandwidth;            // div = p_std * sqrt(2); a true fp32 division, as the CPU reference does
+    int n_experts, min_active;
+};
+
+__device__ __forceinline__ void band_mask_row(float sigma, const MaskGenParams& g, float* __restrict__ out) {
+    // pct = clamp(0.5 * (1 + erf((log sigma - p_mean) / (p_std * sqrt 2))), 0, 1)
+    const float ls = logf(sigma);
+    float pct = __fmul_rn(0.5f, __fadd_rn(1.f, erff(__fdiv_rn(__fsub_rn(ls, g.p_mean), g.div))));
+    pct = fminf(fmaxf(pct, 0.f), 1.f);
+    float dist[HDMOE_MAX_MASK_EXPERTS];
+    unsigned picked = 0;
+#pragma unroll
+    for (int e = 0; e < HDMOE_MAX_MASK_EXPERTS; ++e)
+        if (e < g.n_experts) {
+            dist[e] = fabsf(__fsub_rn(pct, g.centers[e]));
+            out[e] = dist[e] <= g.bandwidth ? 1.f : 0.f;
+        }
+    // the min_active nearest experts are always live (topk(-dist); lowest index wins a tie)
+    for (int m = 0; m < g.min_active && m < g.n_experts; ++m) {
+        int best = -1;
+        float bd = 0.f;
+#pragma unroll
+        for (int e = 0; e < HDMOE_MAX_MASK_EXPERTS; ++e)
+            if (e < g.n_experts && !((picked >> e) & 1u) && (best < 0 || dist[e] < bd)) { best = e; bd = dist[e]; }
+        picked |= 1u << best;
+        out[best] = 1.f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+train_inputs_kernel(const float4* __restrict__ x0, const float4* __restrict__ eps, const float* __restrict__ sigma,
+                    float4* __restrict__ x, long long per4, long long n4, int B, MaskGenParams ga, MaskGenParams gb,
+                    float* __restrict__ mask_a, float* __restrict__ mask_b) {
+    const long long tid = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (tid < B) {
+        const float s = sigma[tid];
+        if (mask_a) band_mask_row(s, ga, mask_a + tid * ga.n_experts);
+        if (mask_b) band_mask_row(s, gb, mask_b + tid * gb.n_experts);
+    }
+    for (long long i = tid; i < n4; i += (long long)gridDim.x * 256) {
+        const float s = sigma[i / per4];
+        const float4 a = x0[i], e = eps[i];
+        x[i] = make_float4(__fadd_rn(a.x, __fmul_rn(e.x, s)), __fadd_rn(a.y, __fmul_rn(e.y, s)),
+                           __fadd_rn(a.z, __fmul_rn(e.z, s)), __fadd_rn(a.w, __fmul_rn(e.w, s)));
+    }
+}
+}  // namespace hdmoe
+
+static int fill_mask_params(hdmoe::MaskGenParams& g, const hdmoe_maskgen_t* m, const char* which) {
+    if (!m) { g.n_experts = 0; g.min_active = 0; return HDMOE_OK; }
+    HDMOE_CHECK_ARG(m->n_experts >= 1 && m->n_experts <= HDMOE_MAX_MASK_EXPERTS, "train_inputs: %s: 1 <= n_experts <= %d",
+                    which, HDMOE_MAX_MASK_EXPERTS);
+    HDMOE_CHECK_ARG(m->min_active >= 0 && m->min_active <= m->n_experts && m->p_std > 0.f, "train_inputs: %s: bad min_active / p_std", which);
+    for (int e = 0; e < m->n_experts; ++e) g.centers[e] = m->centers[e];
+    g.p_mean = m->p_mean;
+    g.div = (float)((double)m->p_std * 1.4142135623730951);     // p_std * np.sqrt(2) in double, then the fp32 division
+    g.bandwidth = m->bandwidth;
+    g.n_experts = m->n_experts;
+    g.min_active = m->min_active;
+    return HDMOE_OK;
+}
+
+extern "C" int hdmoe_train_inputs(const float* x0, const float* eps, const float* sigma, float* x, int B, int64_t per,
+                                  const hdmoe_maskgen_t* gen_a, float* mask_a, const hdmoe_maskgen_t* gen_b, float* mask_b,
+                                  hdmoe_stream_t stream) {
+    HDMOE_CHECK_ARG(x0 && eps && sigma && x && B >= 1 && per >= 4 && per % 4 == 0, "train_inputs: bad args (row length must be a multiple of 4)");
+    HDMOE_CHECK_ARG((gen_a != nullptr) == (mask_a != nullptr) && (gen_b != nullptr) == (mask_b != nullptr),
+                    "train_inputs: a mask generator and its output go together");
+    hdmoe::MaskGenParams ga{}, gb{};
+    int rc = fill_mask_params(ga, gen_a, "gen_a");
+    if (rc != HDMOE_OK) return rc;
+    rc = fill_mask_params(gb, gen_b, "gen_b");
+    if (rc != HDMOE_OK) return rc;
+    const long long n4 = (long long)B * per / 4;
+    int grid = hdmoe::grid_for(n4, 256, 8);
+    if ((long long)grid * 256 < B) grid = (B + 255) / 256;
+    hdmoe::train_inputs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x0, (const float4*)eps, sigma, (float4*)x,
+                                                                        per / 4, n4, B, ga, gb, mask_a, mask_b);
+    HDMOE_CHECK_LAUNCH();
+    return HDMOE_OK;
+}

@@ -624,12 +624,8 @@ extern "C" int hdmoe_vit_block_fwd(const float* tok_in, const float* time, const
         tb.a_off[e] = a_off[e];
         tb.S[e] = tokens[e];
     }
-    static bool attr = false;
-    if (!attr) {
-        HDMOE_CHECK_ARG(cudaFuncSetAttribute(vit_block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(VitSmemFwd)) == cudaSuccess, "vit_block_fwd: shared memory attribute");
-        attr = true;
-    }
+    // per (device, function) attribute: set on every call (cheap), a process may drive several GPUs
+    HDMOE_CHECK_CUDA(cudaFuncSetAttribute(vit_block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VitSmemFwd)));
     vit_block_fwd_kernel<<<(unsigned)rows, kVThreads, sizeof(VitSmemFwd), (cudaStream_t)stream>>>(
         tok_in, time, row_expert, w_hat, aux, tb, final_ln, tok_out);
     HDMOE_CHECK_LAUNCH();
@@ -653,12 +649,8 @@ extern "C" int hdmoe_vit_block_bwd(const float* tok_in, const float* time, const
         tb.a_off[e] = a_off[e];
         tb.S[e] = tokens[e];
     }
-    static bool attr = false;
-    if (!attr) {
-        HDMOE_CHECK_ARG(cudaFuncSetAttribute(vit_block_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(VitSmemBwd)) == cudaSuccess, "vit_block_bwd: shared memory attribute");
-        attr = true;
-    }
+    // per (device, function) attribute: set on every call (cheap), a process may drive several GPUs
+    HDMOE_CHECK_CUDA(cudaFuncSetAttribute(vit_block_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VitSmemBwd)));
     vit_block_bwd_kernel<<<(unsigned)rows, kVThreads, sizeof(VitSmemBwd), (cudaStream_t)stream>>>(
         tok_in, time, row_expert, w_hat, aux, tb, final_ln, d_out, d_tok, d_time, d_w, d_aux);
     HDMOE_CHECK_LAUNCH();

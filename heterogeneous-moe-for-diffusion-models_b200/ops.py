@@ -878,6 +878,36 @@ def sqerr_rows(d, x0):
     return _SqErrRows.apply(d, x0)
 
 
+def train_inputs(x0, eps, sigma, gen_a=None, gen_b=None):
+    """x = x0 + eps * sigma[b] and the band masks of up to two mask generators in ONE launch (csrc/edm_step.cu).
+    gen_* = (centers list, p_mean, p_std, bandwidth at this step, min_active) or None.  Returns (x, mask_a, mask_b)."""
+    _cuda(x0, eps, sigma)
+    x0, eps = _f32c(x0), _f32c(eps)
+    sig = _f32c(sigma).reshape(-1)
+    B, per = x0.shape[0], x0[0].numel()
+    assert sig.numel() == B and eps.shape == x0.shape
+    x = torch.empty_like(x0)
+    descs, masks = [], []
+    for g in (gen_a, gen_b):
+        if g is None:
+            descs.append(None)
+            masks.append(None)
+            continue
+        centers, p_mean, p_std, bw, min_active = g
+        d = L.MaskGenDesc()
+        if len(centers) > L.MAX_MASK_EXPERTS:
+            raise ValueError(f"train_inputs: at most {L.MAX_MASK_EXPERTS} experts per mask generator")
+        for i, c in enumerate(centers):
+            d.centers[i] = float(c)
+        d.p_mean, d.p_std, d.bandwidth, d.n_experts, d.min_active = float(p_mean), float(p_std), float(bw), len(centers), int(min_active)
+        descs.append(d)
+        masks.append(torch.empty(B, len(centers), dtype=torch.float32, device=x0.device))
+    ref = [None if d is None else C.byref(d) for d in descs]
+    L.check(L.lib().hdmoe_train_inputs(_p(x0), _p(eps), _p(sig), _p(x), B, per, ref[0], _p(masks[0]), ref[1], _p(masks[1]),
+                                       _st()), "train_inputs")
+    return x, masks[0], masks[1]
+
+
 # ----------------------------------------------------------------------------------------------------
 # (11) branch scaling (csrc/trunk_glue.cu)
 # ----------------------------------------------------------------------------------------------------

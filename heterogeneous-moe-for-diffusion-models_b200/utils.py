@@ -1,5 +1,6 @@
 """Loss-side router statistics and the host-side producers of the hot path's inputs, with the public
-names of the reference's Utils/utils.py: EDM_LOSS, MaskGenerator, ZetaScheduler, sample_sigma_hybrid."""
+names of the reference's Utils/utils.py: EDM_LOSS, MaskGenerator, ZetaScheduler, sample_sigma_hybrid; plus
+make_train_inputs, the loop body's noise add and both mask generators as one device launch."""
 import math
 from typing import Optional
 
@@ -18,6 +19,22 @@ def sample_sigma_hybrid(batch_size, sigma_min=0.002, sigma_max=80.0, p_mean=-0.4
     un = (torch.rand([n_u, 1, 1, 1], device=device, generator=generator) * (hi - lo) + lo).exp()
     sigma = torch.cat([ln, un], dim=0).clamp(sigma_min, sigma_max)
     return sigma[torch.randperm(batch_size, device=device, generator=generator)]
+
+
+def make_train_inputs(latent, sigma, unet_mask_gen=None, vit_mask_gen=None, step: int = 0, eps=None, generator=None):
+    """The input producers of the reference's loop body (Utils/training.py:133-142) on the device in one launch:
+    `images_noised = latent + randn_like(latent) * sigma` and both router masks `mask_gen(sigma, step)`.
+    `eps` may be supplied (parity runs); otherwise it is drawn with torch's device generator, as the reference does.
+    Returns (images_noised, Unet_mask, vit_mask); a mask is None when its generator is None."""
+    from . import ops
+    if eps is None:
+        eps = torch.randn(latent.shape, device=latent.device, dtype=latent.dtype, generator=generator)
+
+    def desc(g):
+        if g is None:
+            return None
+        return (g._centers_host, g.p_mean, g.p_std, g.bandwidth_scheduler(step), g.min_active)
+    return ops.train_inputs(latent, eps, sigma, desc(unet_mask_gen), desc(vit_mask_gen))
 
 
 class EDM_LOSS(nn.Module):
@@ -135,6 +152,7 @@ class MaskGenerator(nn.Module):
         centers = torch.zeros_like(attrs)
         centers[order] = torch.linspace(noise_range[0], noise_range[1], steps=len(attrs))
         self.register_buffer("expert_centers", centers)
+        self._centers_host = centers.tolist()          # for the fused device producer (no device read per step)
 
     @torch.no_grad()
     def __call__(self, sigma: torch.Tensor, step: int) -> torch.Tensor:

@@ -393,6 +393,24 @@ int hdmoe_sqerr_rows(const float* d, const float* x, float* se, int B, int64_t p
 int hdmoe_sqerr_rows_bwd(const float* d, const float* x, const float* g_se, float* dd, int B, int64_t per,
                          hdmoe_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (13) On-device producers of the train step's inputs, one launch:
+ *      x[b,i] = x0[b,i] + eps[b,i] * sigma[b]            (Utils/training.py:133-134; fp32, product rounded, then sum)
+ *      mask_g[b,e] = |pct(sigma[b]) - centers_g[e]| <= bandwidth_g, and the min_active nearest experts forced live,
+ *      pct = clamp(0.5 (1 + erf((log sigma - p_mean) / (p_std sqrt 2))), 0, 1)   (MaskGenerator, Utils/utils.py:281-309)
+ *      for up to two generators (U-Net and ViT router masks).  `bandwidth` is the value of the host-side
+ *      bandwidth_scheduler at the current step.  Either generator may be NULL (with its mask).
+ * ---------------------------------------------------------------------------------------------- */
+#define HDMOE_MAX_MASK_EXPERTS 16
+typedef struct hdmoe_maskgen {
+    float centers[HDMOE_MAX_MASK_EXPERTS];
+    float p_mean, p_std, bandwidth;
+    int32_t n_experts, min_active;
+} hdmoe_maskgen_t;
+int hdmoe_train_inputs(const float* x0, const float* eps, const float* sigma, float* x, int B, int64_t per,
+                       const hdmoe_maskgen_t* gen_a, float* mask_a, const hdmoe_maskgen_t* gen_b, float* mask_b,
+                       hdmoe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,3 +145,52 @@ def test_scaling_router_fused_matches_oracle(train):
         if train and k.endswith("weights"):
             assert rel_l2(p.detach().cpu(), sd["s." + k].detach()) < 1e-6, k        # forced weight norm (Q6)
     assert torch.allclose(out.sum(1).cpu(), torch.full((B,), 2.0), atol=1e-5)      # rows sum to 2 (test_routers.py:28-29)
+
+
+def _away_from_band_edge(sigma, mg, step, min_active, margin=1e-6):
+    """rows whose mask is decided by more than `margin`: no |dist - bandwidth| and no top-min_active tie inside it"""
+    pct = 0.5 * (1 + torch.erf((torch.log(sigma.flatten().double()) - mg.p_mean) / (mg.p_std * 2 ** 0.5)))
+    dist = (pct.view(-1, 1) - mg.expert_centers.double().view(1, -1)).abs()
+    srt = dist.sort(dim=1).values
+    ok = (dist - mg.bandwidth_scheduler(step)).abs().min(dim=1).values > margin
+    if min_active < dist.shape[1]:
+        ok &= (srt[:, min_active] - srt[:, min_active - 1]) > margin
+    return ok
+
+
+@pytest.mark.gpu
+def test_train_inputs_producer_matches_reference_fixture_and_oracle():
+    """Fused on-device producers (csrc/edm_step.cu train_inputs_kernel): noise add bit-exact, both band masks equal
+    to the reference's MaskGenerator fixtures (tests/golden/producers.npz) at four schedule steps and to the oracle on
+    4 096 random noise levels; a sample whose percentile sits within 1e-6 of a band edge may legitimately fall on
+    either side (device erff / logf vs the CPU's), so those are excluded -- and counted."""
+    from conftest import load_golden
+    from hdmoe_b200.utils import MaskGenerator, make_train_inputs
+    g = load_golden("producers")
+    dev = torch.device("cuda")
+    gens = {}
+    for tag, attrs, rng in (("unet", [3, 3, 5, 5], (0.0, 0.6)), ("vit", [4, 8, 8, 16], (0.4, 1.0))):
+        gens[tag] = MaskGenerator(expert_attributes=attrs, p_mean=-1.2, p_std=1.6, bandwidth=0.3, max_bandwidth=0.8,
+                                  min_active=1, total_steps=5000, step_size=0.1, noise_range=rng, strat_band="step")
+    sigma = g["mask.sigma"]
+    B = sigma.numel()
+    gen = torch.Generator().manual_seed(11)
+    x0, eps = torch.randn(B, 4, 8, 8, generator=gen) * 0.5, torch.randn(B, 4, 8, 8, generator=gen)
+    for step in (0, 700, 2600, 6000):
+        x, mu, mv = make_train_inputs(x0.to(dev), sigma.to(dev), gens["unet"], gens["vit"], step=step, eps=eps.to(dev))
+        assert torch.equal(x.cpu(), x0 + eps * sigma.view(-1, 1, 1, 1))
+        for tag, got in (("unet", mu), ("vit", mv)):
+            ok = _away_from_band_edge(sigma, gens[tag], step, 1)
+            assert int(ok.sum()) >= B - 1
+            assert torch.equal(got.cpu()[ok], g[f"mask.{tag}.{step}"][ok])
+    # wide random sweep against the oracle, min_active = 2, one generator only
+    sig = torch.exp(torch.randn(4096, generator=gen) * 1.6 - 1.2).clamp(0.002, 80.0)
+    mg = MaskGenerator(expert_attributes=[1, 2, 3, 4, 5, 6, 7, 8], p_mean=-1.2, p_std=1.6, bandwidth=0.2, min_active=2)
+    x0b = torch.randn(4096, 4, generator=gen)
+    xb, ma, mb = make_train_inputs(x0b.to(dev), sig.to(dev), mg, None, step=0, eps=torch.zeros(4096, 4, device=dev))
+    assert mb is None and torch.equal(xb.cpu(), x0b)
+    want = O.band_mask(sig, mg.expert_centers, mg.bandwidth_scheduler(0), -1.2, 1.6, min_active=2)
+    safe = _away_from_band_edge(sig, mg, 0, 2)
+    assert int(safe.sum()) > 4000
+    assert torch.equal(ma.cpu()[safe], want[safe])
+    assert bool((ma.sum(1) >= 2).all())
