@@ -130,23 +130,30 @@ plan_count_kernel(PlanSrc src, int T, int E, int ntiles, int G, int32_t* __restr
     if (threadIdx.x < E) tilecnt[(size_t)threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// single block, 1024 threads: exclusive scan of n = E*ntiles ints (expert-major), streamed in coalesced blocks of 4096
-// with a running carry (the round-1 version gave every thread a private contiguous range: uncoalesced, 657 us at T = 1 M)
+// E blocks of 1024 threads: block e turns the per-tile counts of expert e into tile-local exclusive offsets (coalesced
+// blocks of 4096 with a running carry) and writes the expert's total to counts[e]; the expert bases (an exclusive scan
+// over <= 64 totals) are formed by every scatter block in its prologue.  (Round 1 scanned all E * ntiles values in ONE
+// block: 657 us at T = 1 M; the coalesced single-block version still took 38 us of the 68 us plan -- 16 dependent
+// global round trips; one block per expert is one round trip.)
 __global__ void __launch_bounds__(1024)
-plan_scan_kernel(const int32_t* __restrict__ tilecnt, int E, int ntiles, int cap, int32_t* __restrict__ tileoff,
-                 int32_t* __restrict__ counts, int32_t* __restrict__ offsets, int32_t* __restrict__ status) {
+plan_scan_kernel(const int32_t* __restrict__ tilecnt, int ntiles, int32_t* __restrict__ tileoff,
+                 int32_t* __restrict__ counts, int32_t* __restrict__ status) {
     __shared__ int wsum[32];
     __shared__ int carry_s;
-    const int n = E * ntiles;
+    const int32_t* in = tilecnt + (size_t)blockIdx.x * ntiles;
+    int32_t* out = tileoff + (size_t)blockIdx.x * ntiles;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    if (threadIdx.x == 0) {
+        carry_s = 0;
+        if (blockIdx.x == 0) status[0] = 0;
+    }
     __syncthreads();
-    for (int base = 0; base < n; base += 4096) {
+    for (int base = 0; base < ntiles; base += 4096) {
         const int carry = carry_s;       // stable here: written only between the two barriers below
         const int i0 = base + threadIdx.x * 4;
         int v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = i0 + q < n ? tilecnt[i0 + q] : 0;
+        for (int q = 0; q < 4; ++q) v[q] = i0 + q < ntiles ? in[i0 + q] : 0;
         const int s = v[0] + v[1] + v[2] + v[3];
         int incl = s;
 #pragma unroll
@@ -172,20 +179,14 @@ plan_scan_kernel(const int32_t* __restrict__ tilecnt, int E, int ntiles, int cap
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int i = i0 + q;
-            if (i < n) {
-                tileoff[i] = run;
-                if (i % ntiles == 0) offsets[i / ntiles] = run;
+            if (i < ntiles) {
+                out[i] = run;
                 run += v[q];
             }
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        offsets[E] = carry_s;
-        status[0] = carry_s > cap ? 1 : 0;
-    }
-    __syncthreads();
-    if (threadIdx.x < E) counts[threadIdx.x] = offsets[threadIdx.x + 1] - offsets[threadIdx.x];
+    if (threadIdx.x == 0) counts[blockIdx.x] = carry_s;
 }
 
 // rows of tile `tile`; run_s[e] (shared) = first free row of expert e for this tile on entry
@@ -277,15 +278,41 @@ __device__ __forceinline__ void plan_scatter_tile(const PlanSrc& src, int T, int
 
 __global__ void __launch_bounds__(kPlanThreads)
 plan_scatter_kernel(PlanSrc src, int T, int E, int ntiles, int G, int cap, int K,
-                    const int32_t* __restrict__ tileoff, int32_t* __restrict__ row_src,
+                    const int32_t* __restrict__ tileoff, const int32_t* __restrict__ counts,
+                    int32_t* __restrict__ offsets, int32_t* __restrict__ row_src,
                     int32_t* __restrict__ row_expert, float* __restrict__ row_w, int32_t* __restrict__ tok_rows,
                     int32_t* __restrict__ status) {
     __shared__ int warpoff[kPlanThreads / 32][HDMOE_MAX_EXPERTS];
     __shared__ int run_s[HDMOE_MAX_EXPERTS];         // next free row of every expert inside this tile
     __shared__ uint32_t bits[kPlanThreads * HDMOE_MAX_EXPERTS / 32 + 2];
-    if (threadIdx.x < E) run_s[threadIdx.x] = tileoff[(size_t)threadIdx.x * ntiles + blockIdx.x];
+    __shared__ int total_s;
+    // expert bases = exclusive scan over the E totals the scan kernel left in counts[] (E <= 64: one thread, shared memory)
+    if (threadIdx.x < E) run_s[threadIdx.x] = counts[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int e = 0; e < E; ++e) {
+            const int c = run_s[e];
+            run_s[e] = run;
+            run += c;
+        }
+        total_s = run;
+        if (blockIdx.x == 0) {
+            for (int e = 0; e < E; ++e) offsets[e] = run_s[e];
+            offsets[E] = run;
+            if (run > cap) atomicMax(&status[0], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < E) run_s[threadIdx.x] += tileoff[(size_t)threadIdx.x * ntiles + blockIdx.x];
     __syncthreads();
     plan_scatter_tile(src, T, E, blockIdx.x, G, cap, K, row_src, row_expert, row_w, tok_rows, status, warpoff, run_s, bits);
+    // the unused tail [R, cap): well-defined values for fixed-size consumers (was a launch of its own)
+    for (int i = total_s + blockIdx.x * kPlanThreads + threadIdx.x; i < cap; i += gridDim.x * kPlanThreads) {
+        row_src[i] = -1;
+        row_expert[i] = -1;
+        row_w[i] = 0.f;
+    }
 }
 
 // T <= kPlanSmallT: the whole plan (count, offsets, scatter, tail fill) in ONE CTA -- at the reference's own sizes
@@ -318,17 +345,6 @@ plan_small_kernel(PlanSrc src, int T, int E, int cap, int K, int32_t* __restrict
     __syncthreads();
     plan_scatter_tile(src, T, E, 0, G, cap, K, row_src, row_expert, row_w, tok_rows, status, warpoff, run_s, bits);
     for (int i = total_s + threadIdx.x; i < cap; i += kPlanThreads) {
-        row_src[i] = -1;
-        row_expert[i] = -1;
-        row_w[i] = 0.f;
-    }
-}
-
-// fills the unused tail [R, cap) so that fixed-size consumers see well-defined values
-__global__ void plan_tail_kernel(const int32_t* __restrict__ offsets, int E, int cap, int32_t* __restrict__ row_src,
-                                 int32_t* __restrict__ row_expert, float* __restrict__ row_w) {
-    const int R = offsets[E];
-    for (int i = R + blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
         row_src[i] = -1;
         row_expert[i] = -1;
         row_w[i] = 0.f;
@@ -717,10 +733,11 @@ combine_bwd_kernel(const TR* __restrict__ rows, const TY* __restrict__ dY, const
 
 using namespace hdmoe;
 
-// groups of 256 tokens per CTA: keep the (expert, tile) scan array at <= 1024 tiles
+// groups of 256 tokens per CTA: at most 4096 tiles, so that one block of the per-expert scan covers an expert's tile
+// counts in a single coalesced pass (T <= 1 M: one group per tile, the count / scatter blocks have no serial loop)
 static int plan_groups_per_tile(int T) {
     const int ngroups = (T + kPlanThreads - 1) / kPlanThreads;
-    return (ngroups + 1023) / 1024;
+    return (ngroups + 4095) / 4096;
 }
 
 extern "C" size_t hdmoe_dispatch_plan_workspace_bytes(int T, int E) {
@@ -750,12 +767,10 @@ static int dispatch_plan_impl(PlanSrc src, int T, int E, int cap, int K, int32_t
     int32_t* tileoff = tilecnt + (size_t)E * ntiles;
     plan_count_kernel<<<ntiles, kPlanThreads, 0, st>>>(src, T, E, ntiles, G, tilecnt);
     HDMOE_CHECK_LAUNCH();
-    plan_scan_kernel<<<1, 1024, 0, st>>>(tilecnt, E, ntiles, cap, tileoff, counts, offsets, status);
+    plan_scan_kernel<<<E, 1024, 0, st>>>(tilecnt, ntiles, tileoff, counts, status);
     HDMOE_CHECK_LAUNCH();
-    plan_scatter_kernel<<<ntiles, kPlanThreads, 0, st>>>(src, T, E, ntiles, G, cap, K, tileoff, row_src, row_expert, row_w,
-                                                         tok_rows, status);
-    HDMOE_CHECK_LAUNCH();
-    plan_tail_kernel<<<grid_for(cap, 256, 2), 256, 0, st>>>(offsets, E, cap, row_src, row_expert, row_w);
+    plan_scatter_kernel<<<ntiles, kPlanThreads, 0, st>>>(src, T, E, ntiles, G, cap, K, tileoff, counts, offsets, row_src,
+                                                         row_expert, row_w, tok_rows, status);
     HDMOE_CHECK_LAUNCH();
     return HDMOE_OK;
 }
