@@ -163,14 +163,15 @@ class TrainRunner:
     as CUDA graph(s) when possible.  parallelism: "dp" = replicas; "ep" = U-Net experts sharded over the ranks with the
     static-shape all-to-all layer (expert_parallel.py), trunk data-parallel."""
 
-    def __init__(self, variant, res, B, rank, world, device, parallelism="dp", use_graph=True, warmup=3, pinned=False):
+    def __init__(self, variant, res, B, rank, world, device, parallelism="dp", use_graph=True, warmup=3, pinned=False,
+                 ep_transport="peer"):
         import hdmoe_b200
         from hdmoe_b200.optim import FusedAdamW
         from hdmoe_b200.utils import EDM_LOSS
         self.world, self.device, self.B = world, device, B
         self.ep = parallelism == "ep" and world > 1
         if self.ep:
-            hdmoe_b200.enable_expert_parallel([3, 3, 5, 5], capacity_factor=EP_CAPACITY)
+            hdmoe_b200.enable_expert_parallel([3, 3, 5, 5], capacity_factor=EP_CAPACITY, transport=ep_transport)
         else:
             hdmoe_b200.disable_expert_parallel()
         torch.manual_seed(0)
@@ -282,13 +283,18 @@ EP_CAPACITY = 2.0      # rows a rank's experts may receive, in units of T*k (Non
 
 def make_runner(args, variant, res, B, rank, world, device, parallelism, pinned=False):
     """TrainRunner; data-parallel steps are recorded as CUDA graphs.  The expert-parallel step has static shapes and no
-    host synchronisation (it records), but replaying NCCL all-to-alls from inside the graph deadlocked on this
-    torch 2.11 / NCCL 2.28 stack (2 x B200, round-2 log), so it runs eagerly unless --ep-graph is given."""
+    host synchronisation.  With the peer-memory transport (default; csrc/peer.cu) its exchange is plain kernels and the
+    step records like the data-parallel one.  With --ep-transport nccl the all-to-alls are NCCL calls: replaying those
+    from inside the graph deadlocked on this torch 2.11 / NCCL 2.28 stack (2 x B200, round-2 log), so that variant runs
+    eagerly unless --ep-graph is given."""
     ep = parallelism == "ep" and world > 1
-    use_graph = (not args.no_graph) and (not ep or args.ep_graph)
-    r = TrainRunner(variant, res, B, rank, world, device, parallelism, use_graph=use_graph, warmup=args.warmup, pinned=pinned)
-    if ep and not use_graph:
-        r.note = "eager (static-shape expert-parallel step; NCCL-in-graph replay disabled)"
+    transport = getattr(args, "ep_transport", "peer")
+    use_graph = (not args.no_graph) and (not ep or transport == "peer" or args.ep_graph)
+    r = TrainRunner(variant, res, B, rank, world, device, parallelism, use_graph=use_graph, warmup=args.warmup, pinned=pinned,
+                    ep_transport=transport)
+    if ep:
+        r.note += " [expert-parallel exchange: %s]" % ("peer-memory pull kernels + device barrier" if transport == "peer"
+                                                       else "NCCL all_to_all_single")
     return r
 
 
@@ -734,6 +740,8 @@ def config_c_throughput(args, rank, world, device, parallelism, B=64, steps=5):
         fin = bool(torch.isfinite(loss).all())
         if parallelism == "ep":
             EP.check_overflow()
+            from hdmoe_b200 import peer
+            peer.check_all()
         note = r.note
         del r
     except Exception as exc:                          # noqa: BLE001
@@ -755,13 +763,16 @@ def scale_extras(args, rank, world, device):
     samp = {"g1": sampler_throughput(device, rank, world, guidance=1.0)}
     samp["g2"] = sampler_throughput(device, rank, world, guidance=2.0)
     samp.update({k: samp["g1"][k] for k in ("metric", "value", "unit", "batch", "nfe", "ms", "finite")})   # headline: g = 1
+    import copy
     cfg_c = {"dp": config_c_throughput(args, rank, world, device, "dp")}
     if world > 1:
         cfg_c["ep"] = config_c_throughput(args, rank, world, device, "ep")
+        nccl_args = copy.copy(args)
+        nccl_args.ep_transport, nccl_args.ep_graph = "nccl", False
+        cfg_c["ep_nccl_eager"] = config_c_throughput(nccl_args, rank, world, device, "ep")
         # the expert-parallel step runs eagerly (make_runner): the like-for-like bar is the data-parallel step run eagerly
         # too; the difference between the two eager steps is what expert parallelism itself costs, and the exchange
         # timed alone says how much of that is NVLink time
-        import copy
         eager_args = copy.copy(args)
         eager_args.no_graph = True
         cfg_c["dp_eager"] = config_c_throughput(eager_args, rank, world, device, "dp")
@@ -771,8 +782,8 @@ def scale_extras(args, rank, world, device):
             cfg_c["exchange"] = {"error": str(exc)[:200]}
         try:
             cfg_c["ep_over_dp"] = round(cfg_c["ep"]["value"] / cfg_c["dp"]["value"], 3)
-            cfg_c["ep_over_dp_eager"] = round(cfg_c["ep"]["value"] / cfg_c["dp_eager"]["value"], 3)
-            cfg_c["ep_extra_ms_vs_dp_eager"] = round(cfg_c["ep"]["ms_per_step"] - cfg_c["dp_eager"]["ms_per_step"], 2)
+            cfg_c["ep_nccl_eager_over_dp_eager"] = round(cfg_c["ep_nccl_eager"]["value"] / cfg_c["dp_eager"]["value"], 3)
+            cfg_c["ep_extra_ms_vs_dp"] = round(cfg_c["ep"]["ms_per_step"] - cfg_c["dp"]["ms_per_step"], 2)
         except (KeyError, ZeroDivisionError):
             pass
     cfg_c.update({k: cfg_c["dp"].get(k) for k in ("metric", "value", "unit", "ms_per_step", "workload")})
@@ -933,7 +944,9 @@ def main():
     ap.add_argument("--no-sampler", action="store_true", help="skip the EDM sampler throughput extra")
     ap.add_argument("--parallelism", default="dp", choices=["dp", "ep"], help="N>1: data-parallel replicas or expert-parallel U-Net experts")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the whole-step CUDA graph")
-    ap.add_argument("--ep-graph", action="store_true", help="record the expert-parallel step (NCCL all-to-alls inside the graph)")
+    ap.add_argument("--ep-graph", action="store_true", help="record the expert-parallel step even with --ep-transport nccl")
+    ap.add_argument("--ep-transport", default="peer", choices=["peer", "nccl"],
+                    help="expert-parallel exchange: peer-memory kernels (graph-capturable) or NCCL all-to-all (eager)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

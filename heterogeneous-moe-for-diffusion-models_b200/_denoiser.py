@@ -106,22 +106,27 @@ def set_fused_glue(enabled: bool) -> None:
 
 
 # expert parallelism for the U-Net MoE layer; None = every rank runs all experts (pure DP)
-_EP = {"placement": None, "group": None, "capacity_factor": None}
+_EP = {"placement": None, "group": None, "capacity_factor": None, "transport": "nccl"}
 
 
-def enable_expert_parallel(kernel_sizes=None, group=None, placement=None, capacity_factor=None) -> None:
+def enable_expert_parallel(kernel_sizes=None, group=None, placement=None, capacity_factor=None, transport: str = "nccl") -> None:
     """Shard the U-Net experts over the ranks of `group` (cost-balanced); ViT experts stay replicated.
     capacity_factor: rows a rank's experts may receive per layer in units of T*k (None = exact worst case, G*T*k);
-    an overflow sets a device flag that expert_parallel.check_overflow() raises on."""
+    an overflow sets a device flag that expert_parallel.check_overflow() raises on.
+    transport: "nccl" (torch.distributed all-to-all) or "peer" (peer-memory pull kernels behind a device-side barrier,
+    one node; CUDA-graph capturable -- peer.py)."""
+    if transport not in ("nccl", "peer"):
+        raise ValueError("transport must be 'nccl' or 'peer'")
     import torch.distributed as dist
     from . import expert_parallel as EP
     if placement is None:
         placement = EP.ExpertPlacement.balanced(EP.unet_expert_costs(kernel_sizes), dist.get_world_size(group))
-    _EP["placement"], _EP["group"], _EP["capacity_factor"] = placement, group, capacity_factor
+    _EP["placement"], _EP["group"], _EP["capacity_factor"], _EP["transport"] = placement, group, capacity_factor, transport
 
 
 def disable_expert_parallel() -> None:
     _EP["placement"] = _EP["group"] = _EP["capacity_factor"] = None
+    _EP["transport"] = "nccl"
 
 
 def _run_experts_on_rows(experts, plan, xr, tr, txr, nhwc_out: bool = False):
@@ -225,7 +230,7 @@ def router_to_unet_experts(x: torch.Tensor, experts: nn.ModuleList, out_router: 
             return _run_experts_on_rows([experts[i] for i in local_ids], lplan, xr_, tr_, txr_)
 
         out = EP.ep_moe_layer(x, out_router, time_emb, text_emb, run_local, _EP["placement"], k, group=_EP["group"],
-                              payload_dtype=dt, capacity_factor=_EP["capacity_factor"])
+                              payload_dtype=dt, capacity_factor=_EP["capacity_factor"], transport=_EP["transport"])
         return out.permute(0, 2, 3, 1).contiguous() if nhwc_out else out
     if topk is not None and topk[0].shape[0] == out_router.shape[0]:
         plan = ops.dispatch_plan_from_topk(topk[0], topk[1], out_router.shape[1])

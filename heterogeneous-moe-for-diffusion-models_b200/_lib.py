@@ -102,6 +102,8 @@ PROTOTYPES = {
     "hdmoe_scaling_router_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "hdmoe_sqerr_rows": (_i, [_p, _p, _p, _i, _i64, _p]),
     "hdmoe_sqerr_rows_bwd": (_i, [_p, _p, _p, _p, _i, _i64, _p]),
+    "hdmoe_peer_barrier": (_i, [_p, _p, _p, _i, _i, _p]),
+    "hdmoe_peer_pull": (_i, [_p, _p, _i64, _i, _i, _p]),
     "hdmoe_train_inputs": (_i, [_p, _p, _p, _p, _i, _i64, C.POINTER(MaskGenDesc), _p, C.POINTER(MaskGenDesc), _p, _p]),
     "hdmoe_optim_chunk_elems": (_i, []),
     "hdmoe_adamw_step": (_i, [_p, _i, _i, _p, _p, _p, _f, _f, _f, _f, _i, _p]),

@@ -88,7 +88,12 @@ class _AllToAllEq(torch.autograd.Function):
         return out, None
 
 
-def all_to_all_equal(x, group=None):
+def all_to_all_equal(x, group=None, transport: str = "nccl", key=None):
+    """transport "nccl": torch.distributed all_to_all_single; "peer": pull over peer-mapped staging buffers behind a
+    device-side barrier (peer.py / csrc/peer.cu) -- plain kernels, so the layer records into a CUDA graph."""
+    if transport == "peer":
+        from . import peer
+        return peer.all_to_all_equal(x, key, group)
     return _AllToAllEq.apply(x, group)
 
 
@@ -144,7 +149,7 @@ def check_overflow() -> None:
 def ep_moe_layer(x: torch.Tensor, out_router: torch.Tensor, time_emb: torch.Tensor, text_emb: Optional[torch.Tensor],
                  run_local_experts: Callable, placement: ExpertPlacement, top_k: int, group=None,
                  local_ops: Optional[LocalOps] = None, payload_dtype: Optional[torch.dtype] = None,
-                 capacity_factor: Optional[float] = None) -> torch.Tensor:
+                 capacity_factor: Optional[float] = None, transport: str = "nccl", layer_key: str = "unet") -> torch.Tensor:
     """Expert-parallel `router_to_unet_experts` (models/model_config2.py:11-39 semantics on the global batch) with
     STATIC shapes: no host read of split sizes, so the whole layer (and the train step around it) records into a
     CUDA graph.
@@ -205,11 +210,17 @@ def ep_moe_layer(x: torch.Tensor, out_router: torch.Tensor, time_emb: torch.Tens
     srcs = [x.reshape(T, -1).to(dt), time_emb.to(dt)] + ([text_emb.to(dt)] if text_emb is not None else [])
     send = lo.permute(splan, *srcs)                          # each [G * C, D_i]: the all-to-all send buffers
     # 2. per-expert counts of every rank (device)
-    counts_flat = torch.empty(G * E, **i64)
-    dist.all_gather_into_tensor(counts_flat, cnt.contiguous(), group=group)
-    counts_all = counts_flat.view(G, E)
+    if transport == "peer":
+        from . import peer
+        pad = (-E) % 2                                       # 16-byte segments for the pull kernel
+        cnt_p = torch.cat([cnt, cnt.new_zeros(pad)]) if pad else cnt
+        counts_all = peer.all_gather(cnt_p, (layer_key, "counts"), group)[:, :E]
+    else:
+        counts_flat = torch.empty(G * E, **i64)
+        dist.all_gather_into_tensor(counts_flat, cnt.contiguous(), group=group)
+        counts_all = counts_flat.view(G, E)
     # 3. dispatch all-to-alls (equal splits)
-    got = [all_to_all_equal(s_, group) for s_ in send]
+    got = [all_to_all_equal(s_, group, transport, (layer_key, "dispatch", i_)) for i_, s_ in enumerate(send)]
     # 4. compact this rank's rows expert-major
     local_ids = placement.local(rank)
     mine = [j for j, e in enumerate(order) if placement.owner[e] == rank]
@@ -251,5 +262,5 @@ def ep_moe_layer(x: torch.Tensor, out_router: torch.Tensor, time_emb: torch.Tens
     # 5. back to the arrival slots, home, gate-weighted combine
     back_idx = torch.where(live, src_index, torch.full_like(src_index, G * C))
     back = out_flat.new_zeros(G * C + 1, n_img).index_copy(0, back_idx, out_flat)[:G * C]
-    home = all_to_all_equal(back, group)
+    home = all_to_all_equal(back, group, transport, (layer_key, "combine"))
     return lo.combine(home.reshape((G * C,) + img_shape), w_perm, splan, x.dtype)

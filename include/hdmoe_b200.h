@@ -411,6 +411,22 @@ int hdmoe_train_inputs(const float* x0, const float* eps, const float* sigma, fl
                        const hdmoe_maskgen_t* gen_a, float* mask_a, const hdmoe_maskgen_t* gen_b, float* mask_b,
                        hdmoe_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (14) Peer-memory exchange for expert parallelism (the reference has no distributed code).  Buffers are
+ *      mapped into every rank's address space by the host side (CUDA IPC); the pointer tables are DEVICE arrays of
+ *      `world` addresses.  Both calls are plain kernel launches: CUDA-graph capturable, no host state.
+ *   hdmoe_peer_barrier: device-side barrier over all ranks (flag arrays of `world` int32 per rank, zero-initialised;
+ *      `epoch_dev` = 2 int32 of this rank: [0] barriers passed, advanced by the kernel; [1] sticky failure flag, set when
+ *      a peer did not arrive within 8 s -- later barriers then return at once instead of hanging the GPU).  Every rank
+ *      must issue the same sequence.
+ *   hdmoe_peer_pull: dst[g * seg_bytes ...] <- peer g's buffer at byte offset rank_segment * seg_bytes (equal-split
+ *      all-to-all: rank_segment = this rank) or 0 (all-gather: rank_segment = -1), g = 0 .. world-1.
+ * ---------------------------------------------------------------------------------------------- */
+int hdmoe_peer_barrier(int32_t* my_flags, const int64_t* peer_flag_ptrs_dev, int32_t* epoch_dev, int rank, int world,
+                       hdmoe_stream_t stream);
+int hdmoe_peer_pull(void* dst, const int64_t* peer_src_ptrs_dev, int64_t seg_bytes, int rank_segment, int world,
+                    hdmoe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

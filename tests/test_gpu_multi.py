@@ -46,9 +46,11 @@ def _worker(rank, world, port, ret):
         for dt in (torch.float32, torch.bfloat16):
             hdmoe_b200.set_expert_dtype(dt)
             outs = {}
-            for mode in ("local", "ep"):
+            for mode in ("local", "ep", "ep_peer"):
                 if mode == "ep":
                     hdmoe_b200.enable_expert_parallel([3, 3, 5, 5])
+                elif mode == "ep_peer":      # same layer, exchange over peer-mapped buffers (csrc/peer.cu) instead of NCCL
+                    hdmoe_b200.enable_expert_parallel([3, 3, 5, 5], transport="peer")
                 else:
                     hdmoe_b200.disable_expert_parallel()
                 x.grad = None
@@ -57,6 +59,8 @@ def _worker(rank, world, port, ret):
                 out.square().mean().backward()
                 outs[mode] = (out.detach().float().cpu(), x.grad.detach().cpu().clone())
             res[str(dt)] = (rel_l2(outs["ep"][0], outs["local"][0]), rel_l2(outs["ep"][1], outs["local"][1]))
+            # the transport only moves bytes: both expert-parallel variants must agree (1e-6: run-to-run identical kernels)
+            res[str(dt) + ".peer_vs_nccl"] = (rel_l2(outs["ep_peer"][0], outs["ep"][0]), rel_l2(outs["ep_peer"][1], outs["ep"][1]))
         hdmoe_b200.disable_expert_parallel()
         hdmoe_b200.set_expert_dtype(torch.float32)
         ret[rank] = res
@@ -65,7 +69,7 @@ def _worker(rank, world, port, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_expert_parallel_matches_local_experts_nccl():
+def test_expert_parallel_matches_local_experts_nccl_and_peer_transport():
     world, port = 2, _free_port()
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
@@ -76,3 +80,4 @@ def test_expert_parallel_matches_local_experts_nccl():
         # pick other algorithms: fp32 1e-4 (the end-to-end fp32 bar), bf16 2e-2 / 8e-2
         assert r["torch.float32"][0] < 1e-4 and r["torch.float32"][1] < 1e-3, r
         assert r["torch.bfloat16"][0] < 2e-2 and r["torch.bfloat16"][1] < 8e-2, r
+        assert max(r["torch.float32.peer_vs_nccl"]) < 1e-6 and max(r["torch.bfloat16.peer_vs_nccl"]) < 1e-6, r
