@@ -389,7 +389,10 @@ class HDMOEM(nn.Module):
             if trunk is not None:
                 pool_vit, pool_un = trunk([in_vit, in_unet], self.training)
         # the ViT router is evaluated first (RNG order, quirk Q2)
-        if _BRANCH_STREAMS[0] and x.is_cuda and _EP["placement"] is None:
+        # (expert parallelism over NCCL keeps one stream: collectives of concurrently recorded branches must not reorder
+        # between ranks; the peer-memory transport only issues its barriers on the U-Net branch, so the ViT branch may run
+        # beside it)
+        if _BRANCH_STREAMS[0] and x.is_cuda and (_EP["placement"] is None or _EP["transport"] == "peer"):
             # ViT branch (router + MoE layer) beside the U-Net branch; host program order as in the reference
             with _fork(_streams(x.device, "branch", 1)[0], (in_vit, te, text_emb, Vit_router_mask, pool_vit)) as fk:
                 if routed is not None:

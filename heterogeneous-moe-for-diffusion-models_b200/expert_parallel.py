@@ -132,6 +132,9 @@ class LocalRows:
 
 _CONST = {}
 
+# device tensors of the most recent layer call (read by benchmarks / diagnostics after a step; reading synchronises)
+LAST_STATS = {}
+
 # overflow flags of the fixed-capacity exchange (one 0-dim int tensor per layer call; checked lazily by check_overflow)
 _OVERFLOW: List[torch.Tensor] = []
 
@@ -244,6 +247,7 @@ def ep_moe_layer(x: torch.Tensor, out_router: torch.Tensor, time_emb: torch.Tens
     if len(_OVERFLOW) >= 64:
         _OVERFLOW[:] = [torch.stack(_OVERFLOW).max()]
     _OVERFLOW.append((total > capR).to(torch.int32))
+    LAST_STATS.update(recv_rows=total, capacity_rows=capR, sent_rows=send_end[-1], segment_rows=C)
     grows = [g_.index_select(0, src_index) for g_ in got]
     cnt_loc = n_se.sum(0)
     rows = LocalRows(cap=capR, E=n_loc, counts=cnt_loc.to(torch.int32),
