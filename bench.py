@@ -164,14 +164,18 @@ class TrainRunner:
     static-shape all-to-all layer (expert_parallel.py), trunk data-parallel."""
 
     def __init__(self, variant, res, B, rank, world, device, parallelism="dp", use_graph=True, warmup=3, pinned=False,
-                 ep_transport="peer"):
+                 ep_transport="peer", ep_capacity="auto"):
         import hdmoe_b200
         from hdmoe_b200.optim import FusedAdamW
         from hdmoe_b200.utils import EDM_LOSS
         self.world, self.device, self.B = world, device, B
         self.ep = parallelism == "ep" and world > 1
+        self.ep_degree = 1
         if self.ep:
-            hdmoe_b200.enable_expert_parallel([3, 3, 5, 5], capacity_factor=EP_CAPACITY, transport=ep_transport)
+            grp, self.ep_degree = ep_group(rank, world)
+            cap = ep_capacity_for(self.ep_degree) if ep_capacity == "auto" else ep_capacity
+            self.ep_capacity = cap
+            hdmoe_b200.enable_expert_parallel([3, 3, 5, 5], group=grp, capacity_factor=cap, transport=ep_transport)
         else:
             hdmoe_b200.disable_expert_parallel()
         torch.manual_seed(0)
@@ -278,9 +282,27 @@ class TrainRunner:
         return sum(s_.elapsed_time(e_) for s_, e_ in ev)
 
 
-EP_CAPACITY = 1.5      # rows a rank's experts may receive, in units of T*k (None = exact worst case G*T*k); overflow raises.
-                       # Every fixed-shape kernel of the expert path runs over the capacity, so it is sized for the
-                       # imbalance the router produces (reported as recv_rows), not for the worst case
+def ep_capacity_for(degree):
+    """Rows a rank's experts may receive, in units of T*k (None = exact worst case degree*T*k); an overflow is detected on
+    the device and the measurement is repeated at the worst case.  Every fixed-shape kernel of the expert path runs over
+    the capacity, so it is sized for the imbalance a skewed router produces (the busiest expert drawing ~45 % of all rows;
+    the measured figure is reported as recv_rows), not for the worst case."""
+    return min(float(degree), max(1.5, 0.45 * degree))
+
+
+_EP_GROUPS = {}
+
+
+def ep_group(rank, world):
+    """(process group, degree) of the expert-parallel exchange: the four U-Net experts shard over at most 4 ranks; with 8
+    ranks the job is 2 expert-parallel groups of 4 (EP x DP = 4 x 2), the trunk and the gradient all-reduce stay
+    over all ranks."""
+    if world <= 4 or world % 4:
+        return None, world
+    import torch.distributed as dist
+    if world not in _EP_GROUPS:
+        _EP_GROUPS[world] = [dist.new_group(list(range(i, i + 4))) for i in range(0, world, 4)]   # every rank creates all
+    return _EP_GROUPS[world][rank // 4], 4
 
 
 def make_runner(args, variant, res, B, rank, world, device, parallelism, pinned=False):
@@ -293,10 +315,11 @@ def make_runner(args, variant, res, B, rank, world, device, parallelism, pinned=
     transport = getattr(args, "ep_transport", "peer")
     use_graph = (not args.no_graph) and (not ep or transport == "peer" or args.ep_graph)
     r = TrainRunner(variant, res, B, rank, world, device, parallelism, use_graph=use_graph, warmup=args.warmup, pinned=pinned,
-                    ep_transport=transport)
+                    ep_transport=transport, ep_capacity=getattr(args, "ep_capacity", "auto"))
     if ep:
-        r.note += " [expert-parallel exchange: %s]" % ("peer-memory pull kernels + device barrier" if transport == "peer"
-                                                       else "NCCL all_to_all_single")
+        r.note += " [expert-parallel degree %d, exchange: %s, capacity %s x T*k rows]" % (
+            r.ep_degree, "peer-memory pull kernels + device barrier" if transport == "peer" else "NCCL all_to_all_single",
+            r.ep_capacity)
     return r
 
 
@@ -407,26 +430,8 @@ def run_ours(args):
 
     # ---- the other configurations of BASELINE.json at this N (all ranks take part): EDM sampler (configs[3], batch
     # 1024 split over the ranks) and model_config2 at 64x64 (configs[2], batch 64 per GPU), data-parallel and expert-parallel
-    samp = cfg_c = None
-    if not args.no_sampler:
-        del runner, graphed, run_step, step
-        torch.cuda.empty_cache()
-        samp, cfg_c = scale_extras(args, rank, world, device)
-    # every collective is done: release the other ranks before rank 0 measures the single-GPU extras (they must not
-    # sit in an NCCL call for a minute while rank 0 runs the kernel tables and the CPU baseline)
-    if world > 1:
-        import torch.distributed as dist
-        barrier(world)
-        dist.destroy_process_group()
-    line = None
-    if rank == 0:
-        peaks = load_peaks()
-        roof = roofline_gconv(device, peaks, flush)
-        solo = world == 1                            # the sweeps, the sampler and the CPU baseline are N = 1 extras
-        disp = dispatch_sweep(device, peaks, flush, full=args.full_sweep) if solo or args.full_sweep else None
-        cpu = cpu_baseline_train(sample_batch=8, iters=3) if solo else None
-        ref_gpu = ref_cuda_eager(device) if solo and not args.no_sampler else None
-        line = {"metric": "denoiser train img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
+    def make_line(roof, cpu, disp, ref_gpu, peaks_src, samp, cfg_c):
+        return {"metric": "denoiser train img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
                 "ms_per_step_isolated": round(ms_isolated, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -442,8 +447,46 @@ def run_ours(args):
                 "e2e": {"value": round(e2e_value, 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3), "last_loss": loss_host},
                 "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "peaks": peaks["src"],
+                "roofline": roof, "cpu_baseline": cpu, "peaks": peaks_src,
                 "dispatch": disp, "sampler": samp, "config_c": cfg_c, "ref_cuda_eager": ref_gpu}
+
+    samp = cfg_c = None
+    if not args.no_sampler:
+        del runner, graphed, run_step, step
+        torch.cuda.empty_cache()
+        # The extras exercise multi-rank code paths (expert-parallel exchange over peer memory, NCCL sub-groups) that must
+        # never cost the headline measurement: if they do not finish in time every rank leaves, rank 0 first printing the
+        # line with what was measured so far.
+        progress = {"sampler": None, "config_c": None}
+
+        def bail():
+            if rank == 0:
+                progress["timeout"] = "extras did not finish within %d s; partial" % EXTRAS_TIMEOUT_S
+                print(json.dumps(make_line(None, None, None, None, "n/a", progress.get("sampler"),
+                                           dict(progress.get("config_c") or {}, error=progress["timeout"]))), flush=True)
+            os._exit(0)
+
+        import threading
+        wd = threading.Timer(EXTRAS_TIMEOUT_S, bail)
+        wd.daemon = True
+        wd.start()
+        samp, cfg_c = scale_extras(args, rank, world, device, progress)
+        wd.cancel()
+    # every collective is done: release the other ranks before rank 0 measures the single-GPU extras (they must not
+    # sit in an NCCL call for a minute while rank 0 runs the kernel tables and the CPU baseline)
+    if world > 1:
+        import torch.distributed as dist
+        barrier(world)
+        dist.destroy_process_group()
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        roof = roofline_gconv(device, peaks, flush)
+        solo = world == 1                            # the sweeps, the sampler and the CPU baseline are N = 1 extras
+        disp = dispatch_sweep(device, peaks, flush, full=args.full_sweep) if solo or args.full_sweep else None
+        cpu = cpu_baseline_train(sample_batch=8, iters=3) if solo else None
+        ref_gpu = ref_cuda_eager(device) if solo and not args.no_sampler else None
+        line = make_line(roof, cpu, disp, ref_gpu, peaks["src"], samp, cfg_c)
         print(json.dumps(line), flush=True)
     return line
 
@@ -741,13 +784,25 @@ def config_c_throughput(args, rank, world, device, parallelism, B=64, steps=5):
         loss = r.run()
         fin = bool(torch.isfinite(loss).all())
         load = None
-        if parallelism == "ep":
-            EP.check_overflow()
+        if parallelism == "ep" and world > 1:
             from hdmoe_b200 import peer
-            peer.check_all()
+            # every rank must take the same branch: reduce the device-side failure flags before acting on them
+            if max_over_ranks(float(peer.any_failed()), world, device):
+                raise RuntimeError("peer-memory barrier timed out on some rank")
+            if max_over_ranks(float(EP.overflowed()), world, device):
+                if getattr(args, "ep_capacity", "auto") is None:
+                    raise RuntimeError("expert-parallel capacity overflow at the exact worst case (cannot happen)")
+                del r
+                hdmoe_b200.disable_expert_parallel()
+                torch.cuda.empty_cache()
+                import copy
+                worst = copy.copy(args)
+                worst.ep_capacity = None            # exact worst case: degree * T * k rows
+                return config_c_throughput(worst, rank, world, device, parallelism, B, steps)
             st = EP.LAST_STATS
             if "recv_rows" in st:
                 recv = float(st["recv_rows"])
+                # with fewer experts than ranks in the group some ranks receive nothing; balanced = B * k rows per rank
                 load = {"recv_rows_max": max_over_ranks(recv, world, device), "recv_rows_min": -max_over_ranks(-recv, world, device),
                         "rows_per_rank_balanced": B, "capacity_rows": int(st["capacity_rows"]),
                         "imbalance_max_over_mean": round(max_over_ranks(recv, world, device) / B, 3)}
@@ -762,18 +817,26 @@ def config_c_throughput(args, rank, world, device, parallelism, B=64, steps=5):
     hdmoe_b200.disable_expert_parallel()
     torch.cuda.empty_cache()
     return {"metric": "denoiser train img/s", "workload": "model_config2 4x64x64 train step, batch %d per GPU" % B,
-            "parallelism": (f"ep{world} (U-Net experts) + dp{world} (trunk)" if parallelism == "ep" else f"dp{world}"),
+            "parallelism": (f"ep{min(world, 4) if world % 4 == 0 or world < 4 else world} (U-Net experts) + dp{world} (trunk)" if parallelism == "ep" else f"dp{world}"),
             "value": round(B * world / (ms / 1e3), 1), "unit": "img/s", "ms_per_step": round(ms, 2), "execution": note,
             "finite": fin, **({"load": load} if load else {})}
 
 
-def scale_extras(args, rank, world, device):
-    """(sampler, config_c) records of this N; every rank runs them (rank 0 reports)."""
+EXTRAS_TIMEOUT_S = 420
+
+
+def scale_extras(args, rank, world, device, progress=None):
+    """(sampler, config_c) records of this N; every rank runs them (rank 0 reports).  `progress` receives the records as
+    they complete (read by the watchdog of run_ours)."""
+    progress = {} if progress is None else progress
     samp = {"g1": sampler_throughput(device, rank, world, guidance=1.0)}
     samp["g2"] = sampler_throughput(device, rank, world, guidance=2.0)
     samp.update({k: samp["g1"][k] for k in ("metric", "value", "unit", "batch", "nfe", "ms", "finite")})   # headline: g = 1
+    progress["sampler"] = samp
     import copy
     cfg_c = {"dp": config_c_throughput(args, rank, world, device, "dp")}
+    cfg_c.update({k: cfg_c["dp"].get(k) for k in ("metric", "value", "unit", "ms_per_step", "workload")})
+    progress["config_c"] = cfg_c
     if world > 1:
         cfg_c["ep"] = config_c_throughput(args, rank, world, device, "ep")
         nccl_args = copy.copy(args)

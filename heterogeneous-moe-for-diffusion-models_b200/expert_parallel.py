@@ -139,14 +139,21 @@ LAST_STATS = {}
 _OVERFLOW: List[torch.Tensor] = []
 
 
+def overflowed() -> bool:
+    """True if any expert-parallel layer of THIS rank since the last call received more rows than its capacity
+    (synchronises, clears the flags).  Ranks can disagree: reduce the result over the group before acting on it."""
+    bad = False
+    if _OVERFLOW:
+        bad = bool(int(torch.stack(_OVERFLOW).max()))
+        _OVERFLOW.clear()
+    return bad
+
+
 def check_overflow() -> None:
     """Raise if any expert-parallel layer since the last call received more rows than its capacity (synchronises)."""
-    if _OVERFLOW:
-        bad = int(torch.stack(_OVERFLOW).max())
-        _OVERFLOW.clear()
-        if bad:
-            raise RuntimeError("hdmoe_b200 expert parallelism: a rank received more rows than capacity_factor allows; "
-                               "raise capacity_factor (None = exact worst case)")
+    if overflowed():
+        raise RuntimeError("hdmoe_b200 expert parallelism: a rank received more rows than capacity_factor allows; "
+                           "raise capacity_factor (None = exact worst case)")
 
 
 def ep_moe_layer(x: torch.Tensor, out_router: torch.Tensor, time_emb: torch.Tensor, text_emb: Optional[torch.Tensor],

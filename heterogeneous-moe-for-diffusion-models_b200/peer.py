@@ -136,6 +136,11 @@ def all_gather(x: torch.Tensor, key, group=None) -> torch.Tensor:
     return peer_group(group).exchange(x.detach(), ("g",) + tuple(key), gather=True)
 
 
+def any_failed() -> bool:
+    """True if a barrier of any group of this process timed out (synchronises)."""
+    return any(bool(int(pg.epoch[1])) for pg in _GROUPS.values())
+
+
 def check_all() -> None:
     """PeerGroup.check() for every group of this process."""
     for pg in _GROUPS.values():
