@@ -317,7 +317,9 @@ plan_scatter_kernel(PlanSrc src, int T, int E, int ntiles, int G, int cap, int K
 
 // T <= kPlanSmallT: the whole plan (count, offsets, scatter, tail fill) in ONE CTA -- at the reference's own sizes
 // (T = batch = 256 ... 1024) the four-launch version is pure launch latency (19 us against 30 us of data movement)
-constexpr int kPlanSmallT = 4096;
+// (only up to 1024 tokens: at T = 4096 the single CTA takes 35 us at E = 4 and 147 us at E = 64, the three-launch path 15-24 us
+// -- profiles/r2_dispatch_full_sweep.md)
+constexpr int kPlanSmallT = 1024;
 __global__ void __launch_bounds__(kPlanThreads)
 plan_small_kernel(PlanSrc src, int T, int E, int cap, int K, int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
                   int32_t* __restrict__ row_src, int32_t* __restrict__ row_expert, float* __restrict__ row_w,
