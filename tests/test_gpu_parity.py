@@ -148,6 +148,7 @@ def _sparse_from_logits(T, E, k, seed, masked_frac=0.0):
 
 
 @pytest.mark.parametrize("T,E,k,mf", [(8, 4, 1, 0.0), (256, 4, 1, 0.0), (257, 4, 2, 0.5), (1024, 8, 2, 0.3),
+                                      (1025, 4, 1, 0.1), (2000, 8, 2, 0.0), (4096, 64, 1, 0.0),      # first sizes of the 3-launch path
                                       (5000, 64, 2, 0.0), (100000, 16, 1, 0.2), (3, 5, 5, 0.0), (1048576, 64, 2, 0.0)])
 def test_dispatch_plan_bit_exact(T, E, k, mf):
     from hdmoe_b200 import ops
