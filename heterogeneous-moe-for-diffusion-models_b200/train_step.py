@@ -62,6 +62,25 @@ class GraphedTrainStep:
             self.static[k].copy_(v, non_blocking=True)
         self._stage_free.record(main)
 
+    # -- output pipeline: the loss of step i is read on the host while step i + 1 runs ------------------------------
+    def enqueue_loss_read(self) -> int:
+        """After a replay: start the asynchronous D2H copy of the loss into a pinned slot (the static loss tensor is
+        overwritten by the next replay, the slot is not).  Returns the handle for `result`."""
+        if getattr(self, "_pin", None) is None:
+            self._pin = torch.empty(4, dtype=torch.float32).pin_memory()
+            self._pin_ev = [torch.cuda.Event() for _ in range(4)]
+            self._pin_i = 0
+        slot = self._pin_i % 4
+        self._pin_i += 1
+        self._pin[slot:slot + 1].copy_(self.loss.detach().reshape(1).float(), non_blocking=True)
+        self._pin_ev[slot].record()
+        return slot
+
+    def result(self, handle: int) -> float:
+        """The loss a previous `enqueue_loss_read` copied (waits for that copy only, not for later replays)."""
+        self._pin_ev[handle].synchronize()
+        return float(self._pin[handle])
+
     def __call__(self, batch: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
         if batch is not None:
             self.load(batch)
