@@ -15,6 +15,13 @@
 //     TPM taps, 48 cycles at N = 64 (tools/umma_rate.cu, "MN-major LBO=r") instead of 2 x 34.6.  The positions a
 //     shifted atom drops at the end of a strip are padding columns of dY (zero), the ones it adds at the front are a
 //     zeroed lead-in in front of the A box.
+//   * KERNEL ROWS STACKED IN N (round 2).  The B operand is MN-major as well, so an N = nr * KC operand is nr swizzle
+//     atoms LBO bytes apart; with LBO = ONE PADDED IMAGE ROW (Wp positions) atom j is the same input window read one
+//     kernel row further down, i.e. column block j of the accumulator is kernel row tr0 + j.  One M = 128 x N = 128 MMA
+//     then covers up to 128/Cout x 128/KC taps at the full tensor rate (64 cycles) instead of one N = KC MMA per kernel
+//     row at the operand-feed-bound 40 / 48 cycles.  Unlike the forward's tap stacking (tools/legacy/gconv3.cu) nothing
+//     has to be shifted or added afterwards: every (lane block, column block) pair is its own tap of dW.  Only whole
+//     kernel rows are stacked (N = exactly the rows that exist), so no operand read leaves the staged window.
 //   * DOUBLE-BUFFERED ACCUMULATORS.  A tap group is sized to 256 TMEM columns; consecutive items alternate between
 //     the two halves, so the flush (TMEM -> vector atomics, all 128 lanes useful now) of item i runs under the MMAs
 //     of item i + 1.
@@ -22,6 +29,7 @@
 // Everything else follows v1: flattened halo formulation (A = dY strip box with zero-filled surplus columns, B = the
 // zero-padded input window, tap (r, s) reads it at start + (r * Wp + s) rows), item = (row chunk, tap group), split-K
 // over row chunks with `red.global.add.v4.f32`, dynamic item scheduler (last rows first), 4 MMA-issuer warps.
+#include <algorithm>
 #include <type_traits>
 
 #include "tc.cuh"
@@ -51,6 +59,7 @@ constexpr int kW2Stages = 2;
 constexpr int kW2Queue = 8;
 constexpr int kW2Lead = 1024;          // zeroed bytes in front of the A box (>= (TPM-1) position rows)
 constexpr int kW2BufCols = 256;        // TMEM columns per accumulator buffer
+constexpr int kW2MaxUnits = 16;        // units (column-tap block x kernel-row block) per kernel-size class
 
 struct WGrad2Params {
     int n_items, gmax, rows_per_item, cap_rows;
@@ -59,7 +68,6 @@ struct WGrad2Params {
     int cin_pad;
     int n_experts;
     int a_stage_bytes, b_stage_bytes;  // a_stage_bytes includes the lead-in
-    int upg;                           // units (TPM consecutive taps of one kernel row) per tap group
     int cout_total, o_off;             // dY / dW channel count and this launch's first output channel (Cout = 128: 2 passes)
     const int32_t* row_expert;
     const int32_t* n_rows_dev;
@@ -67,8 +75,14 @@ struct WGrad2Params {
     int32_t* sched;                    // [0] next item, [1] finished CTAs (self-resetting, core.cu)
     int32_t wrow[kW2MaxE];
     uint8_t kclass[kW2MaxE];
-    int32_t ksize[kW2Classes], wp[kW2Classes], upr[kW2Classes], nunits[kW2Classes], ngroups[kW2Classes];
+    int32_t ksize[kW2Classes], wp[kW2Classes], ngroups[kW2Classes];
     int32_t a_box_bytes[kW2Classes], b_box_bytes[kW2Classes];
+    // unit i of class c: TPM consecutive taps (columns s0 = u_cu * TPM ...) of the u_nr kernel rows starting at u_tr0;
+    // its accumulators are [chunk][row][KC] columns starting at u_col inside the group's TMEM buffer;
+    // tap group g = units [g_lo[g], g_lo[g + 1])
+    uint8_t u_cu[kW2Classes][kW2MaxUnits], u_tr0[kW2Classes][kW2MaxUnits], u_nr[kW2Classes][kW2MaxUnits];
+    uint16_t u_col[kW2Classes][kW2MaxUnits];
+    uint8_t g_lo[kW2Classes][kW2MaxUnits + 1];
 };
 
 // MN-major operand descriptor: rows are K (positions) of ROWB bytes (64 -> SW64, 128 -> SW128); LBO = byte distance
@@ -217,8 +231,8 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
         // uniform registers; a single-lane loop costs an ELECT + R2UR waterfall per UTCHMMA, see gconv2.cu).
         {
             // D[128 x KC] (+)= A^T B : A, B MN-major (bits 15, 16), M = 128, N = KC, bf16 -> fp32
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                       ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                        ((uint32_t)(128 >> 4) << 24);            // N = nr * KC is added per unit
             const int me = uni(warp) - 1;
             int s = 0, buf = 0;
             uint32_t ph = 0, tph[2] = {0, 0};
@@ -231,8 +245,8 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                 WGT_CNT(5);
                 walk(item, std::true_type{},
                      [&](int r, int e, int kc, int g, int st, int c, bool first) {
-                         const int Wp = uni(p.wp[kc]), upr = uni(p.upr[kc]);
-                         const int u_lo = g * p.upg, u_hi = min(uni(p.nunits[kc]), u_lo + p.upg);
+                         const int Wp = uni(p.wp[kc]);
+                         const int u_lo = uni(p.g_lo[kc][g]), u_hi = uni(p.g_lo[kc][g + 1]);
                          const int nslice = (p.SH * Wp) >> 4;
                          WGT_LAP(1);                             // walk / decode
                          if (need_buf) {
@@ -247,12 +261,13 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                          const uint32_t a0 = s2u(smem + (size_t)s * stage_bytes) + kW2Lead - (TPM - 1) * ROWA;
                          const uint32_t b0 = s2u(smem + (size_t)s * stage_bytes) + p.a_stage_bytes;
                          const uint64_t ad0 = umma_desc_mn2<ROWA>(a0, ROWA);     // atoms one position row apart
-                         const uint64_t bd0 = umma_desc_mn2<ROWB_>(b0, 0);
+                         const uint64_t bd0 = umma_desc_mn2<ROWB_>(b0, (uint32_t)(Wp * ROWB_));   // atoms one image row apart
                          const bool leader = elect_one();
                          for (int u = u_lo + me; u < u_hi; u += kW2Issuers) {
-                             const int tr = u / upr, s0 = (u - tr * upr) * TPM;
-                             const uint32_t d = tmem_base + (uint32_t)(buf * kW2BufCols + ((u - u_lo) * p.nchunks + c) * KC);
-                             const uint64_t bd = bd0 + (uint64_t)(((uint32_t)(tr * Wp + s0) * ROWB_) >> 4);
+                             const int tr0 = uni(p.u_tr0[kc][u]), nr = uni(p.u_nr[kc][u]), s0 = uni(p.u_cu[kc][u]) * TPM;
+                             const uint32_t d = tmem_base + (uint32_t)(buf * kW2BufCols + uni(p.u_col[kc][u]) + c * nr * KC);
+                             const uint64_t bd = bd0 + (uint64_t)(((uint32_t)(tr0 * Wp + s0) * ROWB_) >> 4);
+                             const uint32_t idesc = idesc0 | ((uint32_t)((nr * KC) >> 3) << 17);
                              if (leader) {
 #pragma unroll 4
                                  for (int j = 0; j < nslice; ++j)
@@ -291,27 +306,29 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
             if (item < 0) break;
             walk(item, std::false_type{}, [&](int, int, int, int, int, int, bool) {},
                  [&](int e, int kc, int g) {
-                     const int k = p.ksize[kc], upr = p.upr[kc];
-                     const int u_lo = g * p.upg, u_hi = min(p.nunits[kc], u_lo + p.upg);
+                     const int k = p.ksize[kc];
+                     const int u_lo = p.g_lo[kc][g], u_hi = p.g_lo[kc][g + 1];
                      mb_wait(&t_full[buf], tph[buf]);
                      tph[buf] ^= 1;
                      tc_fence_after();
                      for (int u = u_lo; u < u_hi; ++u) {
-                         const int tr = u / upr, s0 = (u - tr * upr) * TPM;
+                         const int tr0 = p.u_tr0[kc][u], nr = p.u_nr[kc][u], s0 = p.u_cu[kc][u] * TPM;
                          const int ts = s0 + TPM - 1 - a;               // this lane's tap (may lie past the kernel row)
-                         float* drow = p.dW + ((size_t)p.wrow[e] + (size_t)(tr * k + ts) * p.cout_total + p.o_off + o) * p.cin_pad;
+                         const uint32_t ucol = (uint32_t)(buf * kW2BufCols + p.u_col[kc][u]);
                          for (int c = 0; c < p.nchunks; ++c) {
+                             for (int j = 0; j < nr; ++j) {             // column block j = kernel row tr0 + j
+                                 float* drow = p.dW + ((size_t)p.wrow[e] + (size_t)((tr0 + j) * k + ts) * p.cout_total + p.o_off + o) * p.cin_pad;
 #pragma unroll 1
-                             for (int c0 = 0; c0 < KC; c0 += 32) {
-                                 uint32_t v[32];
-                                 tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                               (uint32_t)(buf * kW2BufCols + ((u - u_lo) * p.nchunks + c) * KC + c0), v);
-                                 if (ts < k) {
-                                     float* dst = drow + c * KC + c0;
+                                 for (int c0 = 0; c0 < KC; c0 += 32) {
+                                     uint32_t v[32];
+                                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + ucol + (uint32_t)((c * nr + j) * KC + c0), v);
+                                     if (ts < k) {
+                                         float* dst = drow + c * KC + c0;
 #pragma unroll
-                                     for (int x = 0; x < 8; ++x)
-                                         red_add_v4_2(dst + 4 * x, __uint_as_float(v[4 * x]), __uint_as_float(v[4 * x + 1]),
-                                                      __uint_as_float(v[4 * x + 2]), __uint_as_float(v[4 * x + 3]));
+                                         for (int x = 0; x < 8; ++x)
+                                             red_add_v4_2(dst + 4 * x, __uint_as_float(v[4 * x]), __uint_as_float(v[4 * x + 1]),
+                                                          __uint_as_float(v[4 * x + 2]), __uint_as_float(v[4 * x + 3]));
+                                     }
                                  }
                              }
                          }
@@ -450,20 +467,34 @@ static int gconv_wgrad_pass(const void* X, const void* dY_base, float* dW, int c
     }
     HDMOE_CHECK_ARG(SH > 0, "gconv_wgrad: no strip height fits shared memory for %dx%d, k=%d", H, W, kmax);
     p.SH = SH;
-    // units per tap group: one accumulator buffer is 256 TMEM columns, a unit needs Cin_pad of them
+    // a unit = TPM column taps x nr kernel rows needs nr * Cin_pad TMEM columns; a tap group fills one 256-column buffer
     HDMOE_CHECK_ARG(Cin_pad <= kW2BufCols, "gconv_wgrad: Cin_pad too large for a TMEM accumulator buffer");
-    p.upg = kW2BufCols / Cin_pad;
+    const int nr_max = std::max(1, std::min(128 / KC, kW2BufCols / Cin_pad));      // kernel rows stacked in N (N <= 128)
     int gmax = 1, a_max = 0, b_max = 0;
     for (int c = 0; c < ncls; ++c) {
         const int k = cls_k[c], Wp = pitch(k, SH);
         HDMOE_CHECK_ARG((SH * Wp) % 16 == 0 && Wp <= 256, "gconv_wgrad: strip of %d rows x %d padded columns is not a multiple of 16", SH, Wp);
-        const int upr = (k + TPM - 1) / TPM;                    // units per kernel row
-        const int nunits = k * upr;
-        const int ng = (nunits + p.upg - 1) / p.upg;
+        const int upr = (k + TPM - 1) / TPM;                    // column-tap blocks per kernel row
+        // units in (column block, row block) order, packed greedily into 256-column tap groups
+        int nu = 0, ng = 0, used = kW2BufCols + 1;
+        for (int cu = 0; cu < upr; ++cu)
+            for (int tr0 = 0; tr0 < k; tr0 += nr_max) {
+                const int nr = std::min(nr_max, k - tr0), width = nr * Cin_pad;
+                HDMOE_CHECK_ARG(nu < kW2MaxUnits, "gconv_wgrad: kernel size %d needs more than %d units", k, kW2MaxUnits);
+                if (used + width > kW2BufCols) {
+                    p.g_lo[c][ng++] = (uint8_t)nu;
+                    used = 0;
+                }
+                p.u_cu[c][nu] = (uint8_t)cu;
+                p.u_tr0[c][nu] = (uint8_t)tr0;
+                p.u_nr[c][nu] = (uint8_t)nr;
+                p.u_col[c][nu] = (uint16_t)used;
+                used += width;
+                ++nu;
+            }
+        p.g_lo[c][ng] = (uint8_t)nu;
         p.ksize[c] = k;
         p.wp[c] = Wp;
-        p.upr[c] = upr;
-        p.nunits[c] = nunits;
         p.ngroups[c] = ng;
         p.a_box_bytes[c] = SH * Wp * Cout * 2;
         p.b_box_bytes[c] = (SH + k - 1) * Wp * KC * 2;
