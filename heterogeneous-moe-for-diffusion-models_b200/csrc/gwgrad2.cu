@@ -22,6 +22,11 @@
 //     row at the operand-feed-bound 40 / 48 cycles.  Unlike the forward's tap stacking (tools/legacy/gconv3.cu) nothing
 //     has to be shifted or added afterwards: every (lane block, column block) pair is its own tap of dW.  Only whole
 //     kernel rows are stacked (N = exactly the rows that exist), so no operand read leaves the staged window.
+//   * MMAs DEALT TO THE ISSUER WARPS BY (unit, K slice), all accumulating.  With rows stacked in N a tap group holds
+//     only 2-3 wide units, fewer than issuer warps, and one thread sustains one MMA per ~100 cycles; so every issuer
+//     walks every unit and takes every 4th position slice.  Several warps then feed one accumulator, which forbids a
+//     "first MMA overwrites" flag (no order between warps): every MMA accumulates, and the accumulators are zeroed by
+//     their reader -- once in the prologue, then by the epilogue right after it has read them.
 //   * DOUBLE-BUFFERED ACCUMULATORS.  A tap group is sized to 256 TMEM columns; consecutive items alternate between
 //     the two halves, so the flush (TMEM -> vector atomics, all 128 lanes useful now) of item i runs under the MMAs
 //     of item i + 1.
@@ -145,6 +150,13 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    if (warp > kW2Issuers) {            // epilogue warps: clear both accumulator buffers (all MMAs accumulate)
+        for (int c0 = 0; c0 < 2 * kW2BufCols; c0 += 32) tmem_st32_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + c0);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     const int n_rows = min(*p.n_rows_dev, p.cap_rows);
     const int nstrips = p.H / p.SH;
 
@@ -263,17 +275,21 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                          const uint64_t ad0 = umma_desc_mn2<ROWA>(a0, ROWA);     // atoms one position row apart
                          const uint64_t bd0 = umma_desc_mn2<ROWB_>(b0, (uint32_t)(Wp * ROWB_));   // atoms one image row apart
                          const bool leader = elect_one();
-                         for (int u = u_lo + me; u < u_hi; u += kW2Issuers) {
+                         (void)first;
+                         int j0 = me;                                   // this warp's first slice of the current unit
+                         for (int u = u_lo; u < u_hi; ++u) {
                              const int tr0 = uni(p.u_tr0[kc][u]), nr = uni(p.u_nr[kc][u]), s0 = uni(p.u_cu[kc][u]) * TPM;
                              const uint32_t d = tmem_base + (uint32_t)(buf * kW2BufCols + uni(p.u_col[kc][u]) + c * nr * KC);
                              const uint64_t bd = bd0 + (uint64_t)(((uint32_t)(tr0 * Wp + s0) * ROWB_) >> 4);
                              const uint32_t idesc = idesc0 | ((uint32_t)((nr * KC) >> 3) << 17);
                              if (leader) {
 #pragma unroll 4
-                                 for (int j = 0; j < nslice; ++j)
+                                 for (int j = j0; j < nslice; j += kW2Issuers)
                                      tc_mma(d, ad0 + (uint64_t)((j * 16 * ROWA) >> 4), bd + (uint64_t)((j * 16 * ROWB_) >> 4),
-                                            idesc, !(first && j == 0));
+                                            idesc, 1u);
                              }
+                             // keep the deal round-robin across units: (unit index * nslice + j) % issuers == me
+                             j0 = (j0 + kW2Issuers - (nslice % kW2Issuers)) % kW2Issuers;
                          }
                          if (leader) tc_commit(&empty[s]);
                          __syncwarp();
@@ -321,7 +337,9 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
 #pragma unroll 1
                                  for (int c0 = 0; c0 < KC; c0 += 32) {
                                      uint32_t v[32];
-                                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + ucol + (uint32_t)((c * nr + j) * KC + c0), v);
+                                     const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + ucol + (uint32_t)((c * nr + j) * KC + c0);
+                                     tmem_ld32(ta, v);
+                                     tmem_st32_zero(ta);                 // the next item accumulates into a clean buffer
                                      if (ts < k) {
                                          float* dst = drow + c * KC + c0;
 #pragma unroll
@@ -333,6 +351,7 @@ gwgrad2_kernel(const __grid_constant__ CUtensorMap ta0, const __grid_constant__ 
                              }
                          }
                      }
+                     tmem_wait_st();
                      tc_fence_before();
                      __syncwarp();
                      if (lane == 0) mb_arrive(&t_empty[buf]);
@@ -475,24 +494,39 @@ static int gconv_wgrad_pass(const void* X, const void* dY_base, float* dW, int c
         const int k = cls_k[c], Wp = pitch(k, SH);
         HDMOE_CHECK_ARG((SH * Wp) % 16 == 0 && Wp <= 256, "gconv_wgrad: strip of %d rows x %d padded columns is not a multiple of 16", SH, Wp);
         const int upr = (k + TPM - 1) / TPM;                    // column-tap blocks per kernel row
-        // units in (column block, row block) order, packed greedily into 256-column tap groups
-        int nu = 0, ng = 0, used = kW2BufCols + 1;
+        // units = (column block, row block); packed into 256-column tap groups first-fit by decreasing width (every
+        // group is one more pass over the rows, so as few groups as the TMEM budget allows)
+        struct Unit { int cu, tr0, nr, grp, col; };
+        Unit un[kW2MaxUnits];
+        int nu = 0, ng = 0, fill[kW2MaxUnits] = {0};
         for (int cu = 0; cu < upr; ++cu)
             for (int tr0 = 0; tr0 < k; tr0 += nr_max) {
-                const int nr = std::min(nr_max, k - tr0), width = nr * Cin_pad;
                 HDMOE_CHECK_ARG(nu < kW2MaxUnits, "gconv_wgrad: kernel size %d needs more than %d units", k, kW2MaxUnits);
-                if (used + width > kW2BufCols) {
-                    p.g_lo[c][ng++] = (uint8_t)nu;
-                    used = 0;
-                }
-                p.u_cu[c][nu] = (uint8_t)cu;
-                p.u_tr0[c][nu] = (uint8_t)tr0;
-                p.u_nr[c][nu] = (uint8_t)nr;
-                p.u_col[c][nu] = (uint16_t)used;
-                used += width;
-                ++nu;
+                un[nu++] = Unit{cu, tr0, std::min(nr_max, k - tr0), -1, 0};
             }
-        p.g_lo[c][ng] = (uint8_t)nu;
+        for (int width = nr_max; width >= 1; --width)               // decreasing row count = decreasing column width
+            for (int i = 0; i < nu; ++i) {
+                if (un[i].nr != width) continue;
+                int gsel = 0;
+                while (gsel < ng && fill[gsel] + width * Cin_pad > kW2BufCols) ++gsel;
+                if (gsel == ng) fill[ng++] = 0;
+                un[i].grp = gsel;
+                un[i].col = fill[gsel];
+                fill[gsel] += width * Cin_pad;
+            }
+        int slot = 0;
+        for (int gi = 0; gi < ng; ++gi) {                            // the kernel wants a group's units contiguous
+            p.g_lo[c][gi] = (uint8_t)slot;
+            for (int i = 0; i < nu; ++i)
+                if (un[i].grp == gi) {
+                    p.u_cu[c][slot] = (uint8_t)un[i].cu;
+                    p.u_tr0[c][slot] = (uint8_t)un[i].tr0;
+                    p.u_nr[c][slot] = (uint8_t)un[i].nr;
+                    p.u_col[c][slot] = (uint16_t)un[i].col;
+                    ++slot;
+                }
+        }
+        p.g_lo[c][ng] = (uint8_t)slot;
         p.ksize[c] = k;
         p.wp[c] = Wp;
         p.ngroups[c] = ng;
