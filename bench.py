@@ -819,6 +819,7 @@ def config_c_throughput(args, rank, world, device, parallelism, B=64, steps=5):
                         "rows_per_rank_balanced": B, "capacity_rows": int(st["capacity_rows"]),
                         "imbalance_max_over_mean": round(max_over_ranks(recv, world, device) / B, 3)}
         note = r.note
+        EP.LAST_STATS.clear()                        # device tensors of the recorded step: do not outlive its graph
         del r
     except Exception as exc:                          # noqa: BLE001
         import traceback

@@ -135,17 +135,20 @@ _CONST = {}
 # device tensors of the most recent layer call (read by benchmarks / diagnostics after a step; reading synchronises)
 LAST_STATS = {}
 
-# overflow flags of the fixed-capacity exchange (one 0-dim int tensor per layer call; checked lazily by check_overflow)
-_OVERFLOW: List[torch.Tensor] = []
+# overflow flags of the fixed-capacity exchange: ONE persistent device word per (device, layer), OR-ed into by every layer
+# call with an in-place op -- so a call recorded in a CUDA graph keeps reporting on every replay -- read and cleared by
+# overflowed() / check_overflow()
+_OVERFLOW: dict = {}
 
 
 def overflowed() -> bool:
     """True if any expert-parallel layer of THIS rank since the last call received more rows than its capacity
     (synchronises, clears the flags).  Ranks can disagree: reduce the result over the group before acting on it."""
     bad = False
-    if _OVERFLOW:
-        bad = bool(int(torch.stack(_OVERFLOW).max()))
-        _OVERFLOW.clear()
+    for flag in _OVERFLOW.values():
+        if int(flag):
+            bad = True
+            flag.zero_()
     return bad
 
 
@@ -251,9 +254,10 @@ def ep_moe_layer(x: torch.Tensor, out_router: torch.Tensor, time_emb: torch.Tens
     sr = seg - le * G
     live = j < total
     src_index = torch.where(live, sr * C + src_prefix[sr, le] + (j - seg_off[seg]), torch.zeros_like(j))
-    if len(_OVERFLOW) >= 64:
-        _OVERFLOW[:] = [torch.stack(_OVERFLOW).max()]
-    _OVERFLOW.append((total > capR).to(torch.int32))
+    fk = (str(dev), layer_key)
+    if fk not in _OVERFLOW:              # created by the first (warm-up) call, outside any stream capture
+        _OVERFLOW[fk] = torch.zeros((), dtype=torch.int32, device=dev)
+    _OVERFLOW[fk].copy_(torch.maximum(_OVERFLOW[fk], (total > capR).to(torch.int32)))
     LAST_STATS.update(recv_rows=total, capacity_rows=capR, sent_rows=send_end[-1], segment_rows=C)
     grows = [g_.index_select(0, src_index) for g_ in got]
     cnt_loc = n_se.sum(0)

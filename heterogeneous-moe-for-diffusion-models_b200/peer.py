@@ -109,6 +109,8 @@ _GROUPS: Dict[int, PeerGroup] = {}
 def peer_group(group=None) -> PeerGroup:
     k = id(group) if group is not None else 0
     pg = _GROUPS.get(k)
+    if pg is not None and (pg.world != dist.get_world_size(group) or pg.rank != dist.get_rank(group)):
+        pg = None                                # a new process group re-used the key: map afresh
     if pg is None:
         pg = _GROUPS[k] = PeerGroup(group)
     return pg
