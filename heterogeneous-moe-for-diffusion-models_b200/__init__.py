@@ -9,10 +9,11 @@ from . import _lib, ops  # noqa: F401
 from . import model_internals, model_components, model_config1, model_config2, EDM_sampler, utils  # noqa: F401
 from . import expert_parallel, training  # noqa: F401
 from ._denoiser import (disable_expert_parallel, enable_expert_parallel, get_expert_dtype,  # noqa: F401
-                        set_expert_dtype, set_grouped_experts, set_branch_streams)
+                        set_expert_dtype, set_grouped_experts, set_branch_streams, set_model_options)
 from .EDM_sampler import EDM_Sampler  # noqa: F401
 from .ops import set_gconv_impl  # noqa: F401
 from .router_trunk import set_router_tcgen05_trunk  # noqa: F401
 
 __all__ = ["ops", "model_internals", "model_components", "model_config1", "model_config2", "EDM_sampler", "utils",
-           "EDM_Sampler", "set_expert_dtype", "get_expert_dtype", "set_grouped_experts", "set_branch_streams"]
+           "EDM_Sampler", "set_expert_dtype", "get_expert_dtype", "set_grouped_experts", "set_branch_streams",
+           "set_model_options"]

@@ -105,6 +105,51 @@ def set_fused_glue(enabled: bool) -> None:
     _FUSED_GLUE[0] = bool(enabled)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Per-model options.  The switches above are process-wide defaults; `set_model_options(model, ...)` pins values on ONE
+# model, applied for the duration of that model's forward (and therefore recorded into its autograd graph / CUDA graph),
+# so two models with different settings -- an fp32 teacher next to a bf16 student, a grouped and a per-expert copy in an
+# A/B test -- coexist in one process.
+# ---------------------------------------------------------------------------------------------------------
+_OPTION_CELLS = {"expert_dtype": _EXPERT_DTYPE, "grouped_experts": _GROUPED, "trunk_weight_prep": _TRUNK_PREP,
+                 "sync_free_vit": _SYNC_FREE, "branch_streams": _BRANCH_STREAMS, "fused_glue": _FUSED_GLUE}
+
+
+def set_model_options(model: nn.Module, **options) -> None:
+    """Pin switches on one model (a `preconditioned_HDMOEM` or its `.net`): expert_dtype, grouped_experts,
+    trunk_weight_prep, sync_free_vit, branch_streams, fused_glue.  `None` removes a pin (the process default applies)."""
+    net = getattr(model, "net", model)
+    pins = dict(getattr(net, "_hdmoe_options", None) or {})
+    for k, v in options.items():
+        if k not in _OPTION_CELLS:
+            raise ValueError(f"unknown option {k!r}; known: {sorted(_OPTION_CELLS)}")
+        if k == "expert_dtype" and v is not None and v not in (torch.float32, torch.bfloat16):
+            raise ValueError("expert_dtype must be torch.float32 or torch.bfloat16")
+        if v is None:
+            pins.pop(k, None)
+        else:
+            pins[k] = v if k == "expert_dtype" else bool(v)
+    net.__dict__["_hdmoe_options"] = pins
+
+
+class _model_options:
+    """Context manager: the pins of `net` replace the process defaults inside the block."""
+
+    def __init__(self, net):
+        self.pins = net.__dict__.get("_hdmoe_options") or {}
+
+    def __enter__(self):
+        self.saved = {k: _OPTION_CELLS[k][0] for k in self.pins}
+        for k, v in self.pins.items():
+            _OPTION_CELLS[k][0] = v
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.saved.items():
+            _OPTION_CELLS[k][0] = v
+        return False
+
+
 # expert parallelism for the U-Net MoE layer (SURVEY §8e); None = every rank runs all experts (pure DP)
 _EP = {"placement": None, "group": None, "capacity_factor": None, "transport": "nccl"}
 
@@ -304,6 +349,12 @@ class HDMOEM(nn.Module):
 
     def _forward(self, x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point=None,
                  softness=None, alpha_routing: float = 10, noise: Optional[dict] = None):
+        with _model_options(self):            # this model's pinned switches (set_model_options) for the whole forward
+            return self._forward_pinned(x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point,
+                                        softness, alpha_routing, noise)
+
+    def _forward_pinned(self, x, time_vec, text_emb, Unet_router_mask, Vit_router_mask, zeta, transition_point=None,
+                        softness=None, alpha_routing: float = 10, noise: Optional[dict] = None):
         noise = noise or {}
         if x.is_cuda and _TRUNK_PREP[0]:
             from . import prepared

@@ -226,3 +226,25 @@ def test_checkpoint_file_format_round_trip_and_reference_load(tmp_path):
     ref.load_state_dict(raw["model_state_dict"])           # strict: every key and shape is the reference's
     torch.save({"model_state_dict": ref.state_dict()}, tmp_path / "ref.pt")
     model2.load_state_dict(torch.load(tmp_path / "ref.pt")["model_state_dict"])
+
+
+def test_model_options_pin_and_restore():
+    """set_model_options pins switches on ONE model; the pins apply inside that model's forward only and the process
+    defaults come back afterwards (two models with different settings can coexist)."""
+    from hdmoe_b200 import _denoiser as D
+    torch.manual_seed(0)
+    m = c2.preconditioned_HDMOEM(**TINY)
+    hdmoe_b200.set_model_options(m, expert_dtype=torch.bfloat16, grouped_experts=False)
+    assert m.net._hdmoe_options == {"expert_dtype": torch.bfloat16, "grouped_experts": False}
+    before = (D.get_expert_dtype(), D._GROUPED[0])
+    with D._model_options(m.net):
+        assert D.get_expert_dtype() == torch.bfloat16 and D._GROUPED[0] is False
+    assert (D.get_expert_dtype(), D._GROUPED[0]) == before
+    hdmoe_b200.set_model_options(m, grouped_experts=None)
+    assert m.net._hdmoe_options == {"expert_dtype": torch.bfloat16}
+    with pytest.raises(ValueError):
+        hdmoe_b200.set_model_options(m, no_such_switch=True)
+    with pytest.raises(ValueError):
+        hdmoe_b200.set_model_options(m, expert_dtype=torch.float16)
+    torch.manual_seed(0)
+    assert list(m.state_dict().keys()) == list(c2.preconditioned_HDMOEM(**TINY).state_dict().keys())   # pins are not state

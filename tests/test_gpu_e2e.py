@@ -385,3 +385,36 @@ def test_second_forward_before_backward_is_rejected():
         l3.backward()                                         # the normal order still works afterwards
         assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
     del l2
+
+
+def test_two_models_with_different_pinned_options_coexist():
+    """An fp32 model and a bf16 (grouped tcgen05) model in one process, options pinned per model
+    (hdmoe_b200.set_model_options): each gives exactly what the process-wide switch gives when it runs alone, in either
+    call order, and the process default is untouched."""
+    import hdmoe_b200
+    m32, m16 = _model(2, seed=3).cuda().eval(), _model(2, seed=3).cuda().eval()
+    gen = torch.Generator().manual_seed(5)
+    B = 8
+    x = (torch.randn(B, 4, 32, 32, generator=gen) * 0.5).cuda()
+    sigma = torch.exp(torch.randn(B, 1, 1, 1, generator=gen) * 1.6 - 1.2).clamp(0.002, 80.0).cuda()
+    text = torch.randn(B, 77, 768, generator=gen).cuda()
+    ones = torch.ones(B, 4).cuda()
+
+    def run(m):
+        with torch.no_grad():
+            return m(x=x, sigma=sigma, text_emb=text, Unet_router_mask=ones, Vit_router_mask=ones, zeta=0,
+                     transition_point=-1.2, softness=1.6)["denoised"].float()
+
+    with strict_fp32():
+        assert hdmoe_b200.get_expert_dtype() == torch.float32
+        want32 = run(m32)
+        hdmoe_b200.set_expert_dtype(torch.bfloat16)
+        want16 = run(m16)
+        hdmoe_b200.set_expert_dtype(torch.float32)
+        assert not torch.equal(want32, want16)
+        hdmoe_b200.set_model_options(m16, expert_dtype=torch.bfloat16)
+        hdmoe_b200.set_model_options(m32, expert_dtype=torch.float32)
+        for order in ((m16, m32), (m32, m16)):
+            got = {id(m): run(m) for m in order}
+            assert torch.equal(got[id(m32)], want32) and torch.equal(got[id(m16)], want16)
+        assert hdmoe_b200.get_expert_dtype() == torch.float32
