@@ -64,7 +64,8 @@ constexpr int kW2Stages = 2;
 constexpr int kW2Queue = 8;
 constexpr int kW2Lead = 1024;          // zeroed bytes in front of the A box (>= (TPM-1) position rows)
 constexpr int kW2BufCols = 256;        // TMEM columns per accumulator buffer
-constexpr int kW2MaxUnits = 16;        // units (column-tap block x kernel-row block) per kernel-size class
+constexpr int kW2MaxUnits = 32;        // units (column-tap block x kernel-row block) per kernel-size class (k = 7, Cout = 64,
+                                       // Cin_pad >= 192: 4 column blocks x 7 single rows = 28)
 
 struct WGrad2Params {
     int n_items, gmax, rows_per_item, cap_rows;

@@ -206,7 +206,11 @@ def test_gconv_data_gradient_vs_oracle(shape):
         assert rel_l2(got[r], ref) < 2 * FWD_TOL, (r, e)
 
 
-@pytest.mark.parametrize("shape", [s for s in SHAPES if s[4] in (32, 64, 128) and s[1] % 4 == 0], ids=_ids)
+# weight-gradient-only shapes: wide inputs with a 7x7 expert (one kernel row per unit: the largest unit tables)
+WGRAD_EXTRA = [(2, 8, 8, 256, 64, [7, 3], [1, 1]), (2, 16, 16, 192, 64, [7], [2]), (3, 16, 16, 256, 32, [5, 7], [2, 1])]
+
+
+@pytest.mark.parametrize("shape", [s for s in SHAPES if s[4] in (32, 64, 128) and s[1] % 4 == 0] + WGRAD_EXTRA, ids=_ids)
 def test_gwgrad_vs_oracle(shape):
     """dW_hat[tap][o][c] = sum_{rows of e, pixels} dY[r, q, o] * Xpad[r, q + delta_tap, c] (fp32 accumulators) against
     torch.nn.grad.conv2d_weight in float64 on the same bf16 operands; experts without rows keep a zero block."""
